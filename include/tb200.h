@@ -1,0 +1,175 @@
+/*
+ * tb200.h -- C ABI of libtb200.so: a B200 (sm_100a) backend for the CKKS RNS polynomial hot path
+ * behind tiberate-fhe's CkksEngine.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer named `*_dev` / of type
+ * tb200_poly is DEVICE memory of the context's GPU holding int64 residues in the reference's
+ * layout: a polynomial is int64 [limbs, N] row-major, row i = residues modulo
+ * prime `prime0 + i` in CkksConfig.q order [scale primes..., base prime, special primes...].
+ * All launches go to the caller's stream; functions return 0 on success, a negative TB200_E*
+ * code on bad arguments, a positive cudaError_t on a CUDA failure (tb200_last_error() has text).
+ *
+ * Two layers:
+ *  (1) op layer  -- one entry per operator of the reference's torch op libraries
+ *      (csrc/ops/mont.cpp:138-170, mont_extra.cpp:67-88, ntt_radix2.cpp:29-41,
+ *      intt_radix2.cpp:48-68, he_fused.cpp:80-110); `prime0` replaces the reference's
+ *      "sp_prime_len + right-aligned constant pool" convention: prime0 = P - rows - sp_prime_len
+ *      (SURVEY.md appendix A.0).  tiberate_fhe_b200/wrapper/ maps the reference signatures on it.
+ *  (2) engine layer -- fused, batched entry points for the hot CkksEngine methods
+ *      (tiberate/ckks_engine.py: rescale :1520, cc_mult :1640, relinearize :1695,
+ *      create_switcher :1201, switch_key :1403, rotate_single :1804, pc_mult :2542,
+ *      cc_add_double :1932), bit-exact with the op-by-op reference sequence.
+ */
+#ifndef TB200_H
+#define TB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb200_ctx tb200_ctx;
+typedef void* tb200_stream; /* cudaStream_t */
+
+#define TB200_EINVAL (-1)   /* bad argument (shape / level / alignment) */
+#define TB200_ENOMEM (-2)   /* workspace allocation failed */
+#define TB200_ENODEV (-3)   /* no usable CUDA device */
+
+#define TB200_MAX_GROUPS 32 /* digit groups of a key-switch key (logN17 preset has 13) */
+
+/* A (batched) polynomial: element (b, row, j) lives at ptr[b*batch_stride + row*row_stride + j]. */
+typedef struct {
+  int64_t* ptr;
+  int64_t batch_stride; /* in elements; ignored when batch == 1 */
+  int64_t row_stride;   /* in elements; >= N */
+} tb200_poly;
+
+/* A key-switch key (KeySwitchKey.data, ckks_engine.py:822-860): per GLOBAL digit-group id g the
+ * pair (b_g, a_g), each int64 [P, N] NTT+Montgomery at level 0. Unused ids may be NULL. */
+typedef struct {
+  int32_t num_groups;
+  int32_t reserved;
+  int64_t row_stride;
+  const int64_t* b[TB200_MAX_GROUPS];
+  const int64_t* a[TB200_MAX_GROUPS];
+} tb200_ksk;
+
+/* ---- context (replaces NTTContext + the __constant__ pool: ntt_context.py:151-361,
+ *      constant_mem_context.py:126-295; no 64-prime cap, not process-global) ------------------- */
+tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int num_special,
+                            const int64_t* q /*[num_primes]*/, int scale_bits);
+void tb200_ctx_destroy(tb200_ctx*);
+const char* tb200_last_error(void);
+const char* tb200_version(void);
+/* host copies of derived constants (for tests and for the Python context mirror) */
+int tb200_ctx_get_prime_consts(const tb200_ctx*, int64_t* out /*[num_primes][8]*/);
+int tb200_ctx_get_twiddles(const tb200_ctx*, int inverse, int prime, int64_t* out /*[N], lazy Montgomery form*/);
+int tb200_ctx_info(const tb200_ctx*, int32_t* out /*[8]: logN,N,P,K,LA,LB,device,num_groups*/);
+/* max ciphertexts processed per internal pass by the engine layer (workspace = chunk * ~730 limb rows) */
+int tb200_ctx_set_chunk(tb200_ctx*, int chunk);
+
+/* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */
+enum tb200_pw_op {
+  TB200_MONT_MULT = 0,          /* out = MM(a, b)                      mont_cuda.cu:11-36    */
+  TB200_MONT_ADD = 1,           /* out = CS2(a + b)                    :453-476              */
+  TB200_MONT_SUB = 2,           /* out = CS2(a - b)                    :577-600              */
+  TB200_MONT_ADD_REDUCE_2Q = 3, /* out = CS1(CS2(a + b))               mont_extra_cuda.cu:161 */
+  TB200_MONT_SUB_REDUCE_2Q = 4, /* out = CS1(CS2(a - b))               :230                  */
+  TB200_MONT_ENTER_SCALAR = 5,  /* out = MM(a, scal[row])              mont_cuda.cu:85-109   */
+  TB200_MONT_ENTER_RS = 6,      /* out = MM(a, R^2)                    :151-173              */
+  TB200_MONT_ENTER_RS_SCALE = 7,/* out = MM(a, R^2 2^scale_bits)       :211-234              */
+  TB200_MONT_REDUCE = 8,        /* out = MR(a)                         :345-364              */
+  TB200_REDUCE_2Q = 9,          /* out = CS1(a)                        :402-422              */
+  TB200_MAKE_SIGNED = 10,       /* out = a <= q/2 ? a : a - q          :642-661              */
+  TB200_MAKE_UNSIGNED = 11,     /* out = a + q                         :693-712              */
+  TB200_TILE_UNSIGNED = 12,     /* out[r][j] = a[j] + q_r              :744-760              */
+  TB200_PC_ADD_FUSED = 13,      /* out = CS1(MR(CS2(MM(a,R^2) + b)))   he_fused_cuda.cu:12-51 */
+  TB200_MONT_ENTER_SCALAR_REDUCE_2Q = 14 /* out = CS1(MM(a, scal[row])) mont_extra_cuda.cu:299 */
+};
+/* Generic launcher.  b / scal may be NULL when the op does not use them.  When `explicit_consts`
+ * is non-NULL it points to DEVICE int64 arrays {ql, qh, kl, kh}[rows] (legacy ops that receive
+ * their constants as tensors: mont_enter :272-339, mont_add_legacy :519-571, tile_unsigned);
+ * entries kl/kh may be NULL for ops that only need q. Otherwise row r uses prime prime0 + r. */
+typedef struct {
+  const int64_t* ql;
+  const int64_t* qh;
+  const int64_t* kl;
+  const int64_t* kh;
+  const int64_t* two_q; /* alternative to ql/qh: 2q per row */
+} tb200_explicit_consts;
+int tb200_pointwise(tb200_ctx*, int op, int rows, int batch, int prime0, const tb200_poly* a,
+                    const tb200_poly* b, const int64_t* scal_dev, const tb200_explicit_consts* ec,
+                    const tb200_poly* out, tb200_stream);
+/* out[c][n] = fold_k CS2(acc + in[k][c][n]); pairwise != 0 selects mont_add_many_3d's pair-first
+ * order (mont_extra_cuda.cu:12-42), 0 mont_reduce_add_many_3d (:83-118). in: [K][rows][N] dense. */
+int tb200_add_many(tb200_ctx*, int pairwise, int K, int rows, int prime0, const int64_t* in_dev,
+                   int64_t* out_dev, tb200_stream);
+
+/* ---- op layer: NTT (ntt_radix2_cuda.cu, intt_radix2_cuda.cu, mont_used_in_ntt.cuh) ------------ */
+/* forward, in place on `rows` rows: enter != 0 -> enter_ntt_radix2 (MM by R^2 first, :98-136),
+ * else ntt_radix2 (:49-96). */
+int tb200_ntt(tb200_ctx*, int rows, int batch, int prime0, const tb200_poly* a, int enter, tb200_stream);
+/* inverse, in place: mode 0 intt_radix2 (x N^-1, stays Montgomery), 1 _exit (+MR), 2 _exit_reduce
+ * (+CS1, canonical), 3 _exit_reduce_signed (+centre). intt_radix2_cuda.cu:51-278. */
+int tb200_intt(tb200_ctx*, int rows, int batch, int prime0, const tb200_poly* a, int mode, tb200_stream);
+
+/* ---- op layer: fused HE kernels (he_fused_cuda.cu) ------------------------------------------- */
+/* :99-270. In place on a [rows][N]; row r uses prime prime0 + r; scales_dev[rows]; rescaler_dev[N]. */
+int tb200_rescale_rows(tb200_ctx*, int rows, int prime0, const tb200_poly* a, const int64_t* scales_dev,
+                       const int64_t* rescaler_dev, int64_t round_at, int exact, tb200_stream);
+/* :276-355. state [alpha][N] -> out [rows][N], row r = prime prime0 + r;
+ * l_enter_dev [alpha-1][l_enter_stride], read at column l_enter_offset + r. */
+int tb200_extend(tb200_ctx*, int rows, int prime0, int alpha, const int64_t* state_dev, int64_t state_stride,
+                 const int64_t* l_enter_dev, int64_t l_enter_stride, int64_t l_enter_offset,
+                 int64_t* out_dev, int64_t out_stride, tb200_stream);
+/* :361-427. out[r][perm[j] % N] = CS1(+-a[r][j] + q_r); perm_dev int64 [N]; two_q_dev [rows]. */
+int tb200_codec_rotate(tb200_ctx*, int rows, const tb200_poly* a, const int64_t* perm_dev,
+                       const int64_t* two_q_dev, const tb200_poly* out, tb200_stream);
+/* :433-584. c [rows][N] (ordinary limbs of the level), p [K][N] (special limbs, modified in place by
+ * the chain-backward step exactly as the reference does); out [rows][N]. Constants from the context. */
+int tb200_divide_by_p(tb200_ctx*, int level, const tb200_poly* c, const tb200_poly* p, const tb200_poly* out,
+                      tb200_stream);
+
+/* ---- engine layer (batched; `level` is the level of the INPUT ciphertexts) --------------------- */
+/* rescale :1520-1618.  in: [L+1][N] at `level`, out: [L][N] at level+1 (fresh buffers, not views). */
+int tb200_rescale(tb200_ctx*, int level, int batch, const tb200_poly* in0, const tb200_poly* in1,
+                  const tb200_poly* out0, const tb200_poly* out1, int exact, tb200_stream);
+/* create_switcher :1201-1363 on a coefficient-domain canonical polynomial a [L][N] at `level`. */
+int tb200_keyswitch(tb200_ctx*, int level, int batch, const tb200_poly* a, const tb200_ksk* ksk,
+                    const tb200_poly* out0, const tb200_poly* out1, tb200_stream);
+/* cc_mult (+relinearize) :1640-1732.  a*, b*: [L_in][N] at `level`; with pre_rescale the product
+ * lives at level+1 and has L_in-1 rows.  out0/out1 canonical coefficient domain. */
+int tb200_cc_mult_relin(tb200_ctx*, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,
+                        const tb200_poly* b0, const tb200_poly* b1, const tb200_ksk* evk,
+                        const tb200_poly* out0, const tb200_poly* out1, int pre_rescale, tb200_stream);
+/* cc_mult(post_relin=False): the NTT+Montgomery triplet d0,d1,d2 (:1664-1687). */
+int tb200_cc_mult_triplet(tb200_ctx*, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,
+                          const tb200_poly* b0, const tb200_poly* b1, const tb200_poly* d0,
+                          const tb200_poly* d1, const tb200_poly* d2, int pre_rescale, tb200_stream);
+/* relinearize :1695-1732 on an NTT+Montgomery triplet (inputs are NOT modified). */
+int tb200_relinearize(tb200_ctx*, int level, int batch, const tb200_poly* d0, const tb200_poly* d1,
+                      const tb200_poly* d2, const tb200_ksk* evk, const tb200_poly* out0,
+                      const tb200_poly* out1, tb200_stream);
+/* rotate_single :1804-1840: Galois automorphism X -> X^galois (galois = 3^delta mod 2N, odd) on both
+ * polynomials, then switch_key with rotk.  With ksk == NULL only the automorphism is applied. */
+int tb200_rotate(tb200_ctx*, int level, int batch, int64_t galois, const tb200_poly* c0, const tb200_poly* c1,
+                 const tb200_ksk* rotk, const tb200_poly* out0, const tb200_poly* out1, tb200_stream);
+/* switch_key :1403-1420 (ct.c0 + ks0, ks1). */
+int tb200_switch_key(tb200_ctx*, int level, int batch, const tb200_poly* c0, const tb200_poly* c1,
+                     const tb200_ksk* ksk, const tb200_poly* out0, const tb200_poly* out1, tb200_stream);
+/* pc_mult :2542-2580 with the cached NTT+Montgomery plaintext pt [L][N] (batch stride 0 broadcasts it). */
+int tb200_pc_mult(tb200_ctx*, int level, int batch, const tb200_poly* pt, const tb200_poly* c0,
+                  const tb200_poly* c1, const tb200_poly* out0, const tb200_poly* out1, int post_rescale,
+                  tb200_stream);
+/* cc_add_double :1932-1956 / cc_sub (mont_sub_reduce_2q) */
+int tb200_cc_addsub(tb200_ctx*, int level, int batch, int sub, const tb200_poly* a0, const tb200_poly* a1,
+                    const tb200_poly* b0, const tb200_poly* b1, const tb200_poly* out0, const tb200_poly* out1,
+                    tb200_stream);
+
+/* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
+int64_t tb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TB200_H */

@@ -1,0 +1,292 @@
+"""Host side of the B200 backend: owns the native context and maps tensors onto the C ABI.
+
+Mirrors the roles of the reference's NTTContext + MontgomeryContext + RnsPartition + constant pool
+(tiberate/context/*.py) for the hot path, but every prime-dependent constant is derived inside
+libtb200 (csrc/tb200.cu: tb200_ctx_create), lives in ordinary device memory (no 64-prime cap, not
+process-global) and is addressed by explicit prime index.
+
+Tensors are `torch.int64` CUDA tensors in the reference layout ([limbs, N], optionally with a
+leading batch dimension).  NumPy arrays are accepted only so that tests/emu can drive the
+host-compiled kernels; the product always runs on CUDA tensors.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native
+from ._native import ExplicitConsts, Ksk, Poly, Tb200Error
+
+R_BITS = 62
+R = 1 << R_BITS
+
+
+def _ptr(x) -> int:
+    if x is None:
+        return 0
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()
+
+
+def _strides(x):
+    if isinstance(x, np.ndarray):
+        return [s // x.itemsize for s in x.strides]
+    return list(x.stride())
+
+
+def _is_int64(x) -> bool:
+    if isinstance(x, np.ndarray):
+        return x.dtype == np.int64
+    import torch
+
+    return x.dtype == torch.int64
+
+
+def poly(x, N: int, batched: bool | None = None) -> Poly:
+    """Describe a [rows, N] or [batch, rows, N] int64 tensor (row/batch strides may be views)."""
+    if not _is_int64(x):
+        raise Tb200Error(f"expected an int64 tensor, got {x.dtype}")
+    st = _strides(x)
+    nd = len(st)
+    if x.shape[-1] != N or (x.shape[-1] > 1 and st[-1] != 1):
+        raise Tb200Error(f"last dimension must be N={N} and contiguous, got shape {tuple(x.shape)} strides {st}")
+    if nd == 1:
+        return Poly(_ptr(x), 0, 0)
+    if nd == 2:
+        return Poly(_ptr(x), 0, st[0])
+    if nd == 3:
+        return Poly(_ptr(x), st[0], st[1])
+    raise Tb200Error(f"expected 1, 2 or 3 dimensions, got {nd}")
+
+
+def _stream(x) -> int:
+    if isinstance(x, np.ndarray):
+        return 0
+    import torch
+
+    return torch.cuda.current_stream(x.device).cuda_stream
+
+
+class KeySwitchKeyView:
+    """Pointers of a key-switch key: per global digit group (b, a), each [P, N]. Keeps the tensors alive."""
+
+    def __init__(self, parts, N: int):
+        self.parts = parts
+        k = Ksk()
+        k.num_groups = len(parts)
+        rs = None
+        for g, part in enumerate(parts):
+            if part is None:
+                continue
+            b, a = part
+            for t in (b, a):
+                st = _strides(t)
+                if len(st) != 2 or st[1] != 1 or t.shape[1] != N:
+                    raise Tb200Error("key-switch key parts must be [P, N] row-contiguous int64 tensors")
+                if rs is None:
+                    rs = st[0]
+                elif rs != st[0]:
+                    raise Tb200Error("all key-switch key parts must share one row stride")
+            k.b[g] = _ptr(b)
+            k.a[g] = _ptr(a)
+        k.row_stride = rs if rs is not None else N
+        self.c = k
+
+
+class Tb200Context:
+    """One per (parameter set, GPU).  `lib` defaults to the CUDA library (fails loudly if absent)."""
+
+    def __init__(self, logN: int, q, num_special: int, scale_bits: int = 40, device: int = 0, lib=None):
+        self.lib = lib if lib is not None else _native.get_lib()
+        self.logN, self.N = int(logN), 1 << int(logN)
+        self.q = [int(x) for x in q]
+        self.P, self.K = len(self.q), int(num_special)
+        self.num_ordinary = self.P - self.K
+        self.num_scales = self.num_ordinary - 1
+        self.scale_bits = int(scale_bits)
+        self.device = int(device)
+        qa = np.ascontiguousarray(self.q, dtype=np.int64)
+        h = self.lib.tb200_ctx_create(self.device, self.logN, self.P, self.K, qa.ctypes.data, self.scale_bits)
+        if not h:
+            raise Tb200Error("tb200_ctx_create failed: " + self.lib.tb200_last_error().decode(errors="replace"))
+        self.h = C.c_void_p(h)
+        info = (C.c_int32 * 8)()
+        self.lib.check(self.lib.tb200_ctx_info(self.h, info), "ctx_info")
+        self.LA, self.LB, self.num_groups0 = info[4], info[5], info[7]
+        # host mirror of the Montgomery constants (mont_context.py:26-57) for callers that need them
+        self.k = [(R * pow(R, -1, qi) - 1) // qi for qi in self.q]
+        self.Rs = [R * R % qi for qi in self.q]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection (tests) -----------------------------------------------------------
+    def prime_consts(self) -> np.ndarray:
+        out = np.zeros((self.P, 8), dtype=np.int64)
+        self.lib.check(self.lib.tb200_ctx_get_prime_consts(self.h, out.ctypes.data), "get_prime_consts")
+        return out
+
+    def twiddles(self, inverse: bool, prime: int) -> np.ndarray:
+        out = np.zeros(self.N, dtype=np.int64)
+        self.lib.check(self.lib.tb200_ctx_get_twiddles(self.h, int(inverse), prime, out.ctypes.data), "get_twiddles")
+        return out
+
+    def set_chunk(self, chunk: int):
+        self.lib.check(self.lib.tb200_ctx_set_chunk(self.h, int(chunk)), "set_chunk")
+
+    # ---- level helpers -------------------------------------------------------------------
+    def rows_at(self, level: int, with_special: bool = False) -> int:
+        return (self.P if with_special else self.num_ordinary) - level
+
+    def prime0_for(self, rows: int, sp_prime_len: int) -> int:
+        """a tensor of `rows` rows called with sp_prime_len addresses the
+        constant pool right-aligned: row i -> prime P - rows - sp_prime_len + i."""
+        p0 = self.P - rows - sp_prime_len
+        if p0 < 0:
+            raise Tb200Error(f"{rows} rows with sp_prime_len={sp_prime_len} exceed the {self.P} primes")
+        return p0
+
+    # ---- op layer ------------------------------------------------------------------------
+    def pointwise(self, op: int, a, b=None, out=None, prime0: int = 0, scal=None, ec: ExplicitConsts | None = None):
+        N = self.N
+        pa = poly(a, N)
+        out = a if out is None else out
+        po = poly(out, N)
+        rows = out.shape[-2] if len(out.shape) >= 2 else 1
+        batch = out.shape[0] if len(out.shape) == 3 else 1
+        pb = poly(b, N) if b is not None else None
+        rc = self.lib.tb200_pointwise(self.h, op, rows, batch, prime0, C.byref(pa),
+                                      C.byref(pb) if pb is not None else None, _ptr(scal),
+                                      C.byref(ec) if ec is not None else None, C.byref(po), _stream(out))
+        self.lib.check(rc, f"pointwise op {op}")
+        return out
+
+    def add_many(self, stacked, out, prime0: int, pairwise: bool):
+        K, rows, N = stacked.shape
+        assert N == self.N
+        rc = self.lib.tb200_add_many(self.h, int(pairwise), K, rows, prime0, _ptr(stacked), _ptr(out), _stream(out))
+        self.lib.check(rc, "add_many")
+        return out
+
+    def ntt(self, a, prime0: int, enter: bool, rows: int | None = None):
+        pa = poly(a, self.N)
+        batch = a.shape[0] if len(a.shape) == 3 else 1
+        rows = a.shape[-2] if rows is None else rows
+        self.lib.check(self.lib.tb200_ntt(self.h, rows, batch, prime0, C.byref(pa), int(enter), _stream(a)), "ntt")
+        return a
+
+    def intt(self, a, prime0: int, mode: int, rows: int | None = None):
+        pa = poly(a, self.N)
+        batch = a.shape[0] if len(a.shape) == 3 else 1
+        rows = a.shape[-2] if rows is None else rows
+        self.lib.check(self.lib.tb200_intt(self.h, rows, batch, prime0, C.byref(pa), int(mode), _stream(a)), "intt")
+        return a
+
+    def rescale_rows(self, a, prime0: int, scales, rescaler, round_at: int, exact: bool):
+        pa = poly(a, self.N)
+        rc = self.lib.tb200_rescale_rows(self.h, a.shape[0], prime0, C.byref(pa), _ptr(scales), _ptr(rescaler),
+                                         int(round_at), int(exact), _stream(a))
+        self.lib.check(rc, "rescale_rows")
+        return a
+
+    def extend(self, rns_len: int, prime0: int, state, l_enter, l_enter_offset: int, out):
+        alpha = state.shape[0]
+        le_stride = _strides(l_enter)[0] if (l_enter is not None and alpha > 1) else 0
+        rc = self.lib.tb200_extend(self.h, rns_len, prime0, alpha, _ptr(state), _strides(state)[0],
+                                   _ptr(l_enter) if alpha > 1 else 0, le_stride, int(l_enter_offset), _ptr(out),
+                                   _strides(out)[0], _stream(out))
+        self.lib.check(rc, "extend")
+        return out
+
+    def codec_rotate(self, a, perm, two_q, out):
+        rc = self.lib.tb200_codec_rotate(self.h, a.shape[0], C.byref(poly(a, self.N)), _ptr(perm), _ptr(two_q),
+                                         C.byref(poly(out, self.N)), _stream(out))
+        self.lib.check(rc, "codec_rotate")
+        return out
+
+    def divide_by_p(self, level: int, c, p, out):
+        rc = self.lib.tb200_divide_by_p(self.h, level, C.byref(poly(c, self.N)), C.byref(poly(p, self.N)),
+                                        C.byref(poly(out, self.N)), _stream(out))
+        self.lib.check(rc, "divide_by_p")
+        return out
+
+    # ---- engine layer --------------------------------------------------------------------
+    @staticmethod
+    def _batch(x) -> int:
+        return x.shape[0] if len(x.shape) == 3 else 1
+
+    def _pp(self, x):
+        return C.byref(poly(x, self.N)) if x is not None else None
+
+    def rescale(self, level: int, in0, in1, out0, out1, exact: bool = True):
+        rc = self.lib.tb200_rescale(self.h, level, self._batch(in0), self._pp(in0), self._pp(in1), self._pp(out0),
+                                    self._pp(out1), int(exact), _stream(out0))
+        self.lib.check(rc, "rescale")
+
+    def keyswitch(self, level: int, a, ksk: KeySwitchKeyView, out0, out1):
+        rc = self.lib.tb200_keyswitch(self.h, level, self._batch(a), self._pp(a), C.byref(ksk.c), self._pp(out0),
+                                      self._pp(out1), _stream(out0))
+        self.lib.check(rc, "keyswitch")
+
+    def cc_mult_relin(self, level: int, a0, a1, b0, b1, evk: KeySwitchKeyView, out0, out1, pre_rescale: bool = True):
+        rc = self.lib.tb200_cc_mult_relin(self.h, level, self._batch(a0), self._pp(a0), self._pp(a1), self._pp(b0),
+                                          self._pp(b1), C.byref(evk.c), self._pp(out0), self._pp(out1),
+                                          int(pre_rescale), _stream(out0))
+        self.lib.check(rc, "cc_mult_relin")
+
+    def cc_mult_triplet(self, level: int, a0, a1, b0, b1, d0, d1, d2, pre_rescale: bool = True):
+        rc = self.lib.tb200_cc_mult_triplet(self.h, level, self._batch(a0), self._pp(a0), self._pp(a1), self._pp(b0),
+                                            self._pp(b1), self._pp(d0), self._pp(d1), self._pp(d2), int(pre_rescale),
+                                            _stream(d0))
+        self.lib.check(rc, "cc_mult_triplet")
+
+    def relinearize(self, level: int, d0, d1, d2, evk: KeySwitchKeyView, out0, out1):
+        rc = self.lib.tb200_relinearize(self.h, level, self._batch(d0), self._pp(d0), self._pp(d1), self._pp(d2),
+                                        C.byref(evk.c), self._pp(out0), self._pp(out1), _stream(out0))
+        self.lib.check(rc, "relinearize")
+
+    def rotate(self, level: int, galois: int, c0, c1, rotk: KeySwitchKeyView | None, out0, out1):
+        rc = self.lib.tb200_rotate(self.h, level, self._batch(c0), int(galois), self._pp(c0), self._pp(c1),
+                                   C.byref(rotk.c) if rotk is not None else None, self._pp(out0), self._pp(out1),
+                                   _stream(out0))
+        self.lib.check(rc, "rotate")
+
+    def switch_key(self, level: int, c0, c1, ksk: KeySwitchKeyView, out0, out1):
+        rc = self.lib.tb200_switch_key(self.h, level, self._batch(c0), self._pp(c0), self._pp(c1), C.byref(ksk.c),
+                                       self._pp(out0), self._pp(out1), _stream(out0))
+        self.lib.check(rc, "switch_key")
+
+    def pc_mult(self, level: int, pt, c0, c1, out0, out1, post_rescale: bool = True):
+        ppt = poly(pt, self.N)
+        if len(pt.shape) == 2:
+            ppt.batch_stride = 0
+        rc = self.lib.tb200_pc_mult(self.h, level, self._batch(c0), C.byref(ppt), self._pp(c0), self._pp(c1),
+                                    self._pp(out0), self._pp(out1), int(post_rescale), _stream(out0))
+        self.lib.check(rc, "pc_mult")
+
+    def cc_addsub(self, level: int, sub: bool, a0, a1, b0, b1, out0, out1):
+        rc = self.lib.tb200_cc_addsub(self.h, level, self._batch(a0), int(sub), self._pp(a0), self._pp(a1),
+                                      self._pp(b0), self._pp(b1), self._pp(out0), self._pp(out1), _stream(out0))
+        self.lib.check(rc, "cc_addsub")
+
+
+def galois_element(N: int, delta: int) -> int:
+    """ckks_engine.py:1817-1821: leap = (3^delta - 1)/2 mod 2N, p = 2*leap + 1 = 3^delta mod 2N."""
+    d = delta % N
+    leap = (3 ** d - 1) // 2 % (2 * N)
+    return (2 * leap + 1) % (2 * N)
+
+
+_ = math

@@ -1,0 +1,953 @@
+// tb200.cu -- context construction, launchers and the C ABI declared in include/tb200.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/tb200.h"
+#include "tb200_ctx.h"
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) return fail((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define LAUNCH(kernel, grid, block, stream, ...)               \
+  do {                                                         \
+    TB_LAUNCH(kernel, grid, block, (cudaStream_t)(stream), __VA_ARGS__); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);        \
+  } while (0)
+#define POST()                                                                     \
+  do {                                                                             \
+    cudaError_t e_ = cudaPeekAtLastError();                                        \
+    if (e_ != cudaSuccess) return fail((int)e_, "launch: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* tb200_last_error(void) { return g_err; }
+extern "C" const char* tb200_version(void) { return "tb200 0.1 (sm_100a)"; }
+extern "C" int64_t tb200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static cudaError_t upload(T** dptr, const std::vector<T>& h) {
+  cudaError_t e = cudaMalloc((void**)dptr, h.size() * sizeof(T) + 16);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_primes);
+  cudaFree(c->d_psi4);
+  cudaFree(c->d_ipsi4);
+  cudaFree(c->d_rescale);
+  cudaFree(c->d_pir);
+  cudaFree(c->d_pir_sp);
+  cudaFree(c->d_lenter);
+  cudaFree(c->d_ks);
+  cudaFree(c->ws);
+  delete c;
+}
+
+extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int num_special, const int64_t* q,
+                                       int scale_bits) {
+  if (logN < 8 || logN > 17 || num_special < 1 || num_special > TB_MAXA || num_primes < num_special + 1 || !q) {
+    fail(TB200_EINVAL, "ctx_create: need 8 <= logN <= 17, 1 <= K <= %d, P >= K+1", TB_MAXA);
+    return nullptr;
+  }
+  const int N = 1 << logN, P = num_primes, K = num_special, no = P - K, ns = no - 1;
+  const int np = (ns + K - 1) / K;  // scale-prime groups; + 1 base group
+  if (np + 1 > TB_MAXG) {
+    fail(TB200_EINVAL, "ctx_create: %d digit groups exceed TB200_MAX_GROUPS", np + 1);
+    return nullptr;
+  }
+  for (int g = 0; g < P; ++g) {
+    const u64 qi = (u64)q[g];
+    if (q[g] <= 2 || (qi - 1) % (2ull * N) != 0 || (qi >> 60) > 0) {
+      fail(TB200_EINVAL, "ctx_create: prime %d (%lld) must be = 1 mod 2N and < 2^60", g, (long long)q[g]);
+      return nullptr;
+    }
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fail(TB200_ENODEV, "ctx_create: cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  tb200_ctx* c = new tb200_ctx();
+  c->device = device;
+  c->logN = logN;
+  c->N = N;
+  c->P = P;
+  c->K = K;
+  c->num_ord = no;
+  c->num_levels = no;
+  c->scale_bits = scale_bits;
+  c->LB = logN >= 12 ? 8 : logN / 2;
+  c->LA = logN - c->LB;
+  c->q.assign(q, q + P);
+  c->k.resize(P);
+  c->primes.resize(P);
+  const u128 Rbig = (u128)1 << 62;
+  for (int g = 0; g < P; ++g) {
+    const u64 qi = (u64)q[g];
+    TbPrime& p = c->primes[g];
+    c->k[g] = h_neg_inv_pow2(qi);
+    const u64 Rm = (u64)(Rbig % qi);
+    p.q = (i64)qi;
+    p.q2 = (i64)(2 * qi);
+    p.q4 = 4 * qi;
+    p.k = c->k[g];
+    p.Rs = (i64)h_mulmod(Rm, Rm, qi);
+    p.Rs_scale = (i64)h_mulmod((u64)p.Rs, h_powmod(2, (u64)scale_bits, qi), qi);
+    p.Ninv = (i64)h_mulmod(h_invmod_prime((u64)N, qi), Rm, qi);
+    p.pad = 0;
+  }
+  // twiddles (ntt_context.py:21-85 + psi_enter :277-281)
+  c->psi.resize((size_t)P * N);
+  c->ipsi.resize((size_t)P * N);
+  std::vector<u64> psi4((size_t)P * N), ipsi4((size_t)P * N), series(N);
+  for (int g = 0; g < P; ++g) {
+    const u64 qi = (u64)q[g];
+    const u64 e = (qi - 1) / (2ull * N);
+    u64 w = 0;
+    for (u64 x = 2; x < (u64)N; ++x) {
+      w = h_powmod(x, e, qi);
+      if (h_powmod(w, (u64)N, qi) != 1) break;
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+      const u64 base = dir == 0 ? w : h_invmod_prime(w, qi);
+      u64 acc = 1;
+      for (int i = 0; i < N; ++i) {
+        series[i] = acc;
+        acc = h_mulmod(acc, base, qi);
+      }
+      std::vector<u64>& tab = dir == 0 ? c->psi : c->ipsi;
+      std::vector<u64>& tab4 = dir == 0 ? psi4 : ipsi4;
+      for (int i = 0; i < N; ++i) {
+        const i64 m = h_mm((i64)series[h_bitrev(i, logN)], c->primes[g].Rs, (i64)qi, c->k[g]);
+        tab[(size_t)g * N + i] = (u64)m;
+        tab4[(size_t)g * N + i] = (u64)m << 2;
+      }
+    }
+  }
+  // rescale scales and P_k^-1 tables
+  std::vector<i64> resc((size_t)no * P, 0), pir((size_t)K * P, 0), pirsp((size_t)K * K, 0);
+  for (int l = 0; l < no; ++l)
+    for (int g = l + 1; g < no; ++g) {
+      const u64 qg = (u64)q[g], Rm = (u64)(Rbig % qg);
+      resc[(size_t)l * P + g] = (i64)h_mulmod(h_invmod_prime((u64)q[l] % qg, qg), Rm, qg);
+    }
+  for (int kk = 0; kk < K; ++kk)
+    for (int g = 0; g < no + kk; ++g) {
+      const u64 qg = (u64)q[g], Rm = (u64)(Rbig % qg);
+      pir[(size_t)kk * P + g] = (i64)h_mulmod(h_invmod_prime((u64)q[no + kk] % qg, qg), Rm, qg);
+    }
+  for (int kk = 0; kk < K; ++kk)
+    for (int row = 0; row < kk; ++row) pirsp[(size_t)kk * K + row] = pir[(size_t)kk * P + no + row];
+  // digit groups per level
+  std::vector<i64> lenter;
+  c->ks.resize(no);
+  for (int l = 0; l < no; ++l) {
+    TbKsLevel& lv = c->ks[l];
+    memset(&lv, 0, sizeof(lv));
+    lv.L = no - l;
+    for (int gid = 0; gid <= np; ++gid) {
+      const int lo = gid < np ? gid * K : ns;
+      const int hi = gid < np ? ((gid + 1) * K < ns ? (gid + 1) * K : ns) : ns + 1;
+      std::vector<int> alive;
+      for (int p = lo; p < hi; ++p)
+        if (p >= l) alive.push_back(p);
+      if (alive.empty()) continue;
+      TbKsGroup& G = lv.g[lv.ngroups++];
+      const int alpha = (int)alive.size();
+      G.alpha = alpha;
+      G.first_row = alive[0] - l;
+      G.gid = gid;
+      G.lenter_off = (long)lenter.size();
+      // L_i = m_0 ... m_i reduced modulo whatever prime is needed
+      auto Lmod = [&](int i, u64 m) {
+        u64 r = 1 % m;
+        for (int t = 0; t <= i; ++t) r = h_mulmod(r, (u64)q[alive[t]] % m, m);
+        return r;
+      };
+      for (int i = 0; i + 1 < alpha; ++i) {
+        const u64 m1 = (u64)q[alive[i + 1]];
+        G.Y[i] = (i64)h_mulmod(h_invmod_prime(Lmod(i, m1), m1), (u64)(Rbig % m1), m1);
+        for (int j = i + 2; j < alpha; ++j) {
+          const u64 mj = (u64)q[alive[j]];
+          G.Lsc[i][j] = (i64)h_mulmod(Lmod(i, mj), (u64)(Rbig % mj), mj);
+        }
+      }
+      for (int i = 0; i + 1 < alpha; ++i)
+        for (int g = 0; g < P; ++g) {
+          const u64 qg = (u64)q[g];
+          lenter.push_back((i64)h_mulmod(Lmod(i, qg), (u64)c->primes[g].Rs, qg));
+        }
+    }
+  }
+  if (lenter.empty()) lenter.push_back(0);
+  bool ok = upload(&c->d_primes, c->primes) == cudaSuccess && upload(&c->d_psi4, psi4) == cudaSuccess &&
+            upload(&c->d_ipsi4, ipsi4) == cudaSuccess && upload(&c->d_rescale, resc) == cudaSuccess &&
+            upload(&c->d_pir, pir) == cudaSuccess && upload(&c->d_pir_sp, pirsp) == cudaSuccess &&
+            upload(&c->d_lenter, lenter) == cudaSuccess && upload(&c->d_ks, c->ks) == cudaSuccess;
+  if (!ok) {
+    fail(TB200_ENOMEM, "ctx_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    tb200_ctx_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" int tb200_ctx_get_prime_consts(const tb200_ctx* c, int64_t* out) {
+  if (!c || !out) return fail(TB200_EINVAL, "null");
+  memcpy(out, c->primes.data(), sizeof(TbPrime) * c->P);
+  return 0;
+}
+extern "C" int tb200_ctx_get_twiddles(const tb200_ctx* c, int inverse, int prime, int64_t* out) {
+  if (!c || !out || prime < 0 || prime >= c->P) return fail(TB200_EINVAL, "bad prime index");
+  const std::vector<u64>& t = inverse ? c->ipsi : c->psi;
+  memcpy(out, t.data() + (size_t)prime * c->N, sizeof(u64) * c->N);
+  return 0;
+}
+extern "C" int tb200_ctx_info(const tb200_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(TB200_EINVAL, "null");
+  out[0] = c->logN;
+  out[1] = c->N;
+  out[2] = c->P;
+  out[3] = c->K;
+  out[4] = c->LA;
+  out[5] = c->LB;
+  out[6] = c->device;
+  out[7] = c->ks[0].ngroups;
+  return 0;
+}
+extern "C" int tb200_ctx_set_chunk(tb200_ctx* c, int chunk) {
+  if (!c || chunk < 1) return fail(TB200_EINVAL, "chunk must be >= 1");
+  c->chunk = chunk;
+  return 0;
+}
+
+static int ws_reserve(tb200_ctx* c, size_t elems) {
+  if (elems <= c->ws_elems) return 0;
+  // grow-only; the previous buffer may still be in use by queued kernels of the caller's stream
+  cudaDeviceSynchronize();
+  cudaFree(c->ws);
+  c->ws = nullptr;
+  c->ws_elems = 0;
+  if (cudaMalloc((void**)&c->ws, elems * sizeof(i64)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TB200_ENOMEM, "workspace of %zu MiB could not be allocated", elems * 8 >> 20);
+  }
+  c->ws_elems = elems;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static inline TbView view(const tb200_poly* p) {
+  TbView v;
+  v.p = p ? p->ptr : nullptr;
+  v.bs = p ? (long)p->batch_stride : 0;
+  v.rs = p ? (long)p->row_stride : 0;
+  return v;
+}
+static inline TbView dense(i64* p, long rows, long N) {
+  TbView v;
+  v.p = p;
+  v.bs = rows * N;
+  v.rs = N;
+  return v;
+}
+static int check_poly(const tb200_ctx* c, const tb200_poly* p, const char* name, bool allow_broadcast = false) {
+  if (!p || !p->ptr) return fail(TB200_EINVAL, "%s: null polynomial", name);
+  if (((uintptr_t)p->ptr & 15) != 0) return fail(TB200_EINVAL, "%s: pointer must be 16-byte aligned", name);
+  if (!(allow_broadcast && p->row_stride == 0) && (p->row_stride < c->N || (p->row_stride & 1)))
+    return fail(TB200_EINVAL, "%s: row_stride %lld must be even and >= N", name, (long long)p->row_stride);
+  if (p->batch_stride & 1) return fail(TB200_EINVAL, "%s: batch_stride must be even", name);
+  return 0;
+}
+#define CHECK_POLY(p) \
+  do {                \
+    int rc_ = check_poly(c, p, #p); \
+    if (rc_) return rc_;            \
+  } while (0)
+#define CHECK_ROWS(prime0, rows)                                                                   \
+  if ((rows) < 1 || (prime0) < 0 || (prime0) + (rows) > c->P)                                       \
+  return fail(TB200_EINVAL, "rows %d at prime0 %d outside the %d primes of the context", rows, prime0, c->P)
+
+static inline dim3 grid_pw(const tb200_ctx* c, int rows, int batch, int per_thread) {
+  return dim3((unsigned)((c->N / per_thread + 255) / 256), (unsigned)rows, (unsigned)batch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// op layer
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+static void launch_pw(const tb200_ctx* c, const TbPwArgs& a, int rows, int batch, tb200_stream st) {
+  auto kfn = k_pointwise<OP>;
+  LAUNCH(kfn, grid_pw(c, rows, batch, 2), dim3(c->N / 2 < 256 ? c->N / 2 : 256), st, c->dev(), a);
+}
+
+extern "C" int tb200_pointwise(tb200_ctx* c, int op, int rows, int batch, int prime0, const tb200_poly* a,
+                               const tb200_poly* b, const int64_t* scal, const tb200_explicit_consts* ec,
+                               const tb200_poly* out, tb200_stream st) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  if (op < 0 || op > 14) return fail(TB200_EINVAL, "unknown pointwise op %d", op);
+  if (batch < 1) return fail(TB200_EINVAL, "batch must be >= 1");
+  const bool has_b = op <= 4 || op == 13;
+  const bool needs_scal = op == 5 || op == 14;
+  const bool explicit_c = ec && (ec->ql || ec->two_q);
+  if (!explicit_c) CHECK_ROWS(prime0, rows);
+  if (rows < 1) return fail(TB200_EINVAL, "rows must be >= 1");
+  {
+    int rc = check_poly(c, a, "a", op == TB200_TILE_UNSIGNED);
+    if (rc) return rc;
+  }
+  CHECK_POLY(out);
+  if (has_b) CHECK_POLY(b);
+  if (needs_scal && !scal) return fail(TB200_EINVAL, "op %d needs a per-row scalar tensor", op);
+  if (explicit_c && !ec->two_q && !ec->qh) return fail(TB200_EINVAL, "explicit constants need ql and qh");
+  const bool needs_k = op == 0 || (op >= 5 && op <= 8) || op >= 13;
+  if (explicit_c && needs_k && !(ec->kl && ec->kh) ) return fail(TB200_EINVAL, "op %d needs kl/kh", op);
+  if (explicit_c && (op == 6 || op == 7 || op == 13))
+    return fail(TB200_EINVAL, "op %d takes its constants from the context only", op);
+  CK(cudaSetDevice(c->device));
+  TbPwArgs g;
+  g.a = view(a);
+  g.b = has_b ? view(b) : view(a);
+  g.out = view(out);
+  g.scal = scal;
+  g.ql = explicit_c ? ec->ql : nullptr;
+  g.qh = explicit_c ? ec->qh : nullptr;
+  g.kl = explicit_c ? ec->kl : nullptr;
+  g.kh = explicit_c ? ec->kh : nullptr;
+  g.two_q = explicit_c ? ec->two_q : nullptr;
+  g.prime0 = prime0;
+  g.N = c->N;
+  switch (op) {
+#define PWCASE(n) \
+  case n:         \
+    launch_pw<n>(c, g, rows, batch, st); \
+    break;
+    PWCASE(0) PWCASE(1) PWCASE(2) PWCASE(3) PWCASE(4) PWCASE(5) PWCASE(6) PWCASE(7) PWCASE(8) PWCASE(9) PWCASE(10)
+    PWCASE(11) PWCASE(12) PWCASE(13) PWCASE(14)
+#undef PWCASE
+  }
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_add_many(tb200_ctx* c, int pairwise, int K, int rows, int prime0, const int64_t* in,
+                              int64_t* out, tb200_stream st) {
+  if (!c || !in || !out || K < 1) return fail(TB200_EINVAL, "add_many: bad arguments");
+  CHECK_ROWS(prime0, rows);
+  CK(cudaSetDevice(c->device));
+  LAUNCH(k_add_many, grid_pw(c, rows, 1, 1), dim3(256), st, c->dev(), (const i64*)in, (i64*)out, K, rows, c->N,
+         prime0, pairwise);
+  POST();
+  return 0;
+}
+
+// ---- NTT ----------------------------------------------------------------------------------------
+static inline int ntt_lw(const tb200_ctx* c) {  // log2 of the column width of a pass-A tile
+  int lw = 12 - c->LA;
+  if (lw > c->LB) lw = c->LB;
+  return lw;
+}
+
+template <int PRO>
+static int launch_fwd_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, tb200_stream st) {
+  const int lw = ntt_lw(c);
+  const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
+  switch (c->LA) {
+#define ACASE(n)                                            \
+  case n: {                                                 \
+    auto kfn = k_ntt_fwd_A<n, PRO>;                         \
+    LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
+  } break;
+    ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
+#undef ACASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LA %d", c->LA);
+  }
+  return 0;
+}
+template <int EPI>
+static int launch_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, tb200_stream st) {
+  const int lw = ntt_lw(c);
+  const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
+  switch (c->LA) {
+#define ACASE(n)                                            \
+  case n: {                                                 \
+    auto kfn = k_ntt_inv_A<n, EPI>;                         \
+    LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
+  } break;
+    ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
+#undef ACASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LA %d", c->LA);
+  }
+  return 0;
+}
+static int launch_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
+                    tb200_stream st) {
+  const int te = c->N < TB_TILE ? c->N : TB_TILE;
+  const dim3 grid((unsigned)(c->N / te), (unsigned)rows, (unsigned)batch), block((unsigned)(te / 16));
+  switch (c->LB) {
+#define BCASE(n)                                                 \
+  case n: {                                                      \
+    if (inverse) {                                               \
+      auto kfn = k_ntt_inv_B<n>;                                 \
+      LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0);  \
+    } else {                                                     \
+      auto kfn = k_ntt_fwd_B<n>;                                 \
+      LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0);  \
+    }                                                            \
+  } break;
+    BCASE(4) BCASE(5) BCASE(6) BCASE(7) BCASE(8)
+#undef BCASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LB %d", c->LB);
+  }
+  return 0;
+}
+
+static int ntt_forward(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, bool enter,
+                       tb200_stream st) {
+  int rc = enter ? launch_fwd_A<TB_PRO_ENTER>(c, src, dst, rows, batch, prime0, st)
+                 : launch_fwd_A<TB_PRO_NONE>(c, src, dst, rows, batch, prime0, st);
+  if (rc) return rc;
+  return launch_B(c, false, dst, dst, rows, batch, prime0, st);
+}
+static int ntt_inverse(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, int mode,
+                       tb200_stream st) {
+  int rc = launch_B(c, true, src, dst, rows, batch, prime0, st);
+  if (rc) return rc;
+  switch (mode) {
+    case 0:
+      return launch_inv_A<TB_EPI_NINV>(c, dst, dst, rows, batch, prime0, st);
+    case 1:
+      return launch_inv_A<TB_EPI_EXIT>(c, dst, dst, rows, batch, prime0, st);
+    case 2:
+      return launch_inv_A<TB_EPI_EXIT_REDUCE>(c, dst, dst, rows, batch, prime0, st);
+    case 3:
+      return launch_inv_A<TB_EPI_EXIT_SIGNED>(c, dst, dst, rows, batch, prime0, st);
+  }
+  return fail(TB200_EINVAL, "intt mode %d", mode);
+}
+
+extern "C" int tb200_ntt(tb200_ctx* c, int rows, int batch, int prime0, const tb200_poly* a, int enter,
+                         tb200_stream st) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  CHECK_ROWS(prime0, rows);
+  CHECK_POLY(a);
+  if (batch < 1) return fail(TB200_EINVAL, "batch must be >= 1");
+  CK(cudaSetDevice(c->device));
+  int rc = ntt_forward(c, view(a), view(a), rows, batch, prime0, enter != 0, st);
+  if (rc) return rc;
+  POST();
+  return 0;
+}
+extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const tb200_poly* a, int mode,
+                          tb200_stream st) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  CHECK_ROWS(prime0, rows);
+  CHECK_POLY(a);
+  if (batch < 1 || mode < 0 || mode > 3) return fail(TB200_EINVAL, "bad batch/mode");
+  CK(cudaSetDevice(c->device));
+  int rc = ntt_inverse(c, view(a), view(a), rows, batch, prime0, mode, st);
+  if (rc) return rc;
+  POST();
+  return 0;
+}
+
+// ---- fused HE ops ---------------------------------------------------------------------------------
+extern "C" int tb200_rescale_rows(tb200_ctx* c, int rows, int prime0, const tb200_poly* a, const int64_t* scales,
+                                  const int64_t* rescaler, int64_t round_at, int exact, tb200_stream st) {
+  if (!c || !scales || !rescaler) return fail(TB200_EINVAL, "rescale_rows: null argument");
+  CHECK_ROWS(prime0, rows);
+  CHECK_POLY(a);
+  if (((uintptr_t)rescaler & 15) != 0) return fail(TB200_EINVAL, "rescaler must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  TbView r;
+  r.p = (i64*)rescaler;
+  r.bs = 0;
+  r.rs = 0;
+  LAUNCH(k_rescale, grid_pw(c, rows, 1, 2), dim3(c->N / 2 < 256 ? c->N / 2 : 256), st, c->dev(), view(a), r, view(a),
+         (const i64*)scales, prime0, c->N, (i64)round_at, exact);
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_extend(tb200_ctx* c, int rows, int prime0, int alpha, const int64_t* state, int64_t state_stride,
+                            const int64_t* l_enter, int64_t le_stride, int64_t le_off, int64_t* out,
+                            int64_t out_stride, tb200_stream st) {
+  if (!c || !state || !out || alpha < 1 || (alpha > 1 && !l_enter)) return fail(TB200_EINVAL, "extend: bad arguments");
+  CHECK_ROWS(prime0, rows);
+  CK(cudaSetDevice(c->device));
+  LAUNCH(k_extend_op, grid_pw(c, rows, 1, 1), dim3(256), st, c->dev(), (const i64*)state, (long)state_stride, alpha,
+         (const i64*)l_enter, (long)le_stride, (long)le_off, (i64*)out, (long)out_stride, prime0, c->N);
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_codec_rotate(tb200_ctx* c, int rows, const tb200_poly* a, const int64_t* perm,
+                                  const int64_t* two_q, const tb200_poly* out, tb200_stream st) {
+  if (!c || !perm || !two_q || rows < 1) return fail(TB200_EINVAL, "codec_rotate: bad arguments");
+  CHECK_POLY(a);
+  CHECK_POLY(out);
+  if (a->ptr == out->ptr) return fail(TB200_EINVAL, "codec_rotate cannot run in place");
+  CK(cudaSetDevice(c->device));
+  LAUNCH(k_codec_rotate_op, grid_pw(c, rows, 1, 1), dim3(256), st, view(a), (const i64*)perm, (const i64*)two_q,
+         view(out), c->N);
+  POST();
+  return 0;
+}
+
+static int moddown(tb200_ctx* c, int level, int batch, TbView cc, TbView p, TbView add, TbView out, int tail,
+                   tb200_stream st) {
+  const int L = c->num_ord - level;
+  LAUNCH(k_chain_backward, grid_pw(c, 1, batch, 1), dim3(256), st, c->dev(), p, (const i64*)c->d_pir_sp, c->K,
+         c->num_ord, c->N);
+  const dim3 grid = grid_pw(c, L, batch, 1);
+  if (tail == 0) {
+    LAUNCH(k_divide_by_p<0>, grid, dim3(256), st, c->dev(), cc, p, add, out, (const i64*)c->d_pir, c->K, level, c->N);
+  } else if (tail == 1) {
+    LAUNCH(k_divide_by_p<1>, grid, dim3(256), st, c->dev(), cc, p, add, out, (const i64*)c->d_pir, c->K, level, c->N);
+  } else {
+    LAUNCH(k_divide_by_p<2>, grid, dim3(256), st, c->dev(), cc, p, add, out, (const i64*)c->d_pir, c->K, level, c->N);
+  }
+  return 0;
+}
+
+extern "C" int tb200_divide_by_p(tb200_ctx* c, int level, const tb200_poly* cc, const tb200_poly* p,
+                                 const tb200_poly* out, tb200_stream st) {
+  if (!c || level < 0 || level >= c->num_ord) return fail(TB200_EINVAL, "divide_by_p: bad level");
+  CHECK_POLY(cc);
+  CHECK_POLY(p);
+  CHECK_POLY(out);
+  CK(cudaSetDevice(c->device));
+  int rc = moddown(c, level, 1, view(cc), view(p), view(cc), view(out), 0, st);
+  if (rc) return rc;
+  POST();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// engine layer
+// ------------------------------------------------------------------------------------------------
+static int check_level(const tb200_ctx* c, int level, int batch) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  if (level < 0 || level >= c->num_ord) return fail(TB200_EINVAL, "level %d outside [0, %d)", level, c->num_ord);
+  if (batch < 1) return fail(TB200_EINVAL, "batch must be >= 1");
+  return 0;
+}
+static inline TbView shift(TbView v, long b) {
+  v.p += b * v.bs;
+  return v;
+}
+
+static int rescale_impl(tb200_ctx* c, int level, int batch, TbView in, TbView out, int exact, tb200_stream st) {
+  const int L = c->num_ord - level - 1;  // rows kept
+  TbView body = in;
+  body.p += in.rs;  // rows 1..L
+  LAUNCH(k_rescale, grid_pw(c, L, batch, 2), dim3(c->N / 2 < 256 ? c->N / 2 : 256), st, c->dev(), body, in, out,
+         (const i64*)(c->d_rescale + (size_t)level * c->P + level + 1), level + 1, c->N, (i64)(c->q[level] / 2), exact);
+  return 0;
+}
+
+extern "C" int tb200_rescale(tb200_ctx* c, int level, int batch, const tb200_poly* in0, const tb200_poly* in1,
+                             const tb200_poly* out0, const tb200_poly* out1, int exact, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (level + 1 >= c->num_ord) return fail(TB200_EINVAL, "rescale: level %d is the last level", level);
+  CHECK_POLY(in0);
+  CHECK_POLY(out0);
+  CK(cudaSetDevice(c->device));
+  rescale_impl(c, level, batch, view(in0), view(out0), exact, st);
+  if (in1) {
+    CHECK_POLY(in1);
+    CHECK_POLY(out1);
+    rescale_impl(c, level, batch, view(in1), view(out1), exact, st);
+  }
+  POST();
+  return 0;
+}
+
+static int make_key(const tb200_ctx* c, int level, const tb200_ksk* k, TbKskDev* out) {
+  if (!k) return fail(TB200_EINVAL, "null key-switch key");
+  if (k->row_stride < c->N || (k->row_stride & 1)) return fail(TB200_EINVAL, "ksk row_stride");
+  memset(out, 0, sizeof(*out));
+  out->rs = (long)k->row_stride;
+  const TbKsLevel& lv = c->ks[level];
+  for (int gi = 0; gi < lv.ngroups; ++gi) {
+    const int gid = lv.g[gi].gid;
+    if (gid >= k->num_groups || !k->b[gid] || !k->a[gid])
+      return fail(TB200_EINVAL, "key-switch key lacks digit group %d needed at level %d", gid, level);
+    if ((((uintptr_t)k->b[gid]) | ((uintptr_t)k->a[gid])) & 15) return fail(TB200_EINVAL, "ksk alignment");
+    out->b[gid] = (const i64*)k->b[gid];
+    out->a[gid] = (const i64*)k->a[gid];
+  }
+  return 0;
+}
+
+// workspace elements needed by the key switch of one ciphertext at `level`
+static size_t ks_ws_elems(const tb200_ctx* c, int level) {
+  const size_t L = c->num_ord - level, E = L + c->K, ng = c->ks[level].ngroups;
+  return (L + ng * E + 2 * E) * (size_t)c->N;
+}
+
+// key switch of `nb` polynomials (nb <= chunk). a: coefficient canonical [L][N].
+// tail: 0 -> out0 = ks0 ; 1 -> out0 = CS1(add0 + ks0), out1 = CS1(add1 + ks1) ; 2 -> out0 = CS1(CS2(add0 + ks0)), out1 = ks1
+static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKskDev& key, TbView add0, TbView add1,
+                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st) {
+  const int N = c->N, L = c->num_ord - level, E = L + c->K;
+  const TbKsLevel& lv = c->ks[level];
+  const int ng = lv.ngroups;
+  const TbKsLevel* dlv = c->d_ks + level;
+  i64* state = ws;
+  i64* ext = state + (size_t)nb * L * N;
+  i64* acc = ext + (size_t)nb * ng * E * N;
+  const TbDev d = c->dev();
+  // 1. digits
+  LAUNCH(k_digits, dim3((unsigned)((N + 255) / 256), (unsigned)ng, (unsigned)nb), dim3(256), st, d, dlv, a,
+         dense(state, L, N), level, N);
+  // 2. extend every group to the L+K limbs
+  LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
+         dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, dense(state, L, N), ext, level, N, E);
+  // 3. NTT (stages only) of the nb*ng extended polynomials
+  int rc = ntt_forward(c, dense(ext, E, N), dense(ext, E, N), E, nb * ng, level, false, st);
+  if (rc) return rc;
+  // 4. inner product with the key, accumulated over groups
+  LAUNCH(k_mac, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)nb), dim3(N / 2 < 256 ? N / 2 : 256), st,
+         d, dlv, key, (const i64*)ext, acc, level, N, E);
+  // 5. back to coefficients, canonical
+  rc = ntt_inverse(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, 2, st);
+  if (rc) return rc;
+  // 6. ModDown (+ fused tail)
+  for (int h = 0; h < 2; ++h) {
+    TbView cc;
+    cc.p = acc + (size_t)h * E * N;
+    cc.bs = 2L * E * N;
+    cc.rs = N;
+    TbView p = cc;
+    p.p += (size_t)L * N;
+    const int t = (tail == 2 && h == 1) ? 0 : tail;
+    rc = moddown(c, level, nb, cc, p, h == 0 ? add0 : add1, h == 0 ? out0 : out1, t, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int tb200_keyswitch(tb200_ctx* c, int level, int batch, const tb200_poly* a, const tb200_ksk* ksk,
+                               const tb200_poly* out0, const tb200_poly* out1, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  CHECK_POLY(a);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  TbKskDev key;
+  if ((rc = make_key(c, level, ksk, &key))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * ch))) return rc;
+  for (int b0 = 0; b0 < batch; b0 += ch) {
+    const int nb = batch - b0 < ch ? batch - b0 : ch;
+    rc = keyswitch_chunk(c, level, nb, shift(view(a), b0), key, shift(view(a), b0), shift(view(a), b0),
+                         shift(view(out0), b0), shift(view(out1), b0), 0, c->ws, st);
+    if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_switch_key(tb200_ctx* c, int level, int batch, const tb200_poly* c0, const tb200_poly* c1,
+                                const tb200_ksk* ksk, const tb200_poly* out0, const tb200_poly* out1,
+                                tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  CHECK_POLY(c0);
+  CHECK_POLY(c1);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  TbKskDev key;
+  if ((rc = make_key(c, level, ksk, &key))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * ch))) return rc;
+  for (int b0 = 0; b0 < batch; b0 += ch) {
+    const int nb = batch - b0 < ch ? batch - b0 : ch;
+    rc = keyswitch_chunk(c, level, nb, shift(view(c1), b0), key, shift(view(c0), b0), shift(view(c0), b0),
+                         shift(view(out0), b0), shift(view(out1), b0), 2, c->ws, st);
+    if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, const tb200_poly* c0,
+                            const tb200_poly* c1, const tb200_ksk* rotk, const tb200_poly* out0,
+                            const tb200_poly* out1, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  CHECK_POLY(c0);
+  CHECK_POLY(c1);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  if (!(galois & 1) || galois < 1 || galois >= 2 * (int64_t)c->N)
+    return fail(TB200_EINVAL, "galois element must be odd and in [1, 2N)");
+  if (c0->ptr == out0->ptr || c1->ptr == out1->ptr) return fail(TB200_EINVAL, "rotate cannot run in place");
+  CK(cudaSetDevice(c->device));
+  const int N = c->N, L = c->num_ord - level;
+  const dim3 grid = grid_pw(c, L, 1, 1);
+  if (!rotk) {
+    for (int b = 0; b < batch; ++b) {
+      LAUNCH(k_automorphism, grid, dim3(256), st, c->dev(), shift(view(c0), b), shift(view(out0), b), level, (i64)galois);
+      LAUNCH(k_automorphism, grid, dim3(256), st, c->dev(), shift(view(c1), b), shift(view(out1), b), level, (i64)galois);
+    }
+    POST();
+    return 0;
+  }
+  TbKskDev key;
+  if ((rc = make_key(c, level, rotk, &key))) return rc;
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  const size_t rot_elems = 2 * (size_t)L * N;  // rotated c0, c1 per ciphertext
+  if ((rc = ws_reserve(c, (ks_ws_elems(c, level) + rot_elems) * ch))) return rc;
+  for (int b0 = 0; b0 < batch; b0 += ch) {
+    const int nb = batch - b0 < ch ? batch - b0 : ch;
+    i64* r0 = c->ws;
+    i64* r1 = r0 + (size_t)nb * L * N;
+    i64* ksws = r1 + (size_t)nb * L * N;
+    const dim3 gridb((unsigned)((N + 255) / 256), (unsigned)L, (unsigned)nb);
+    LAUNCH(k_automorphism, gridb, dim3(256), st, c->dev(), shift(view(c0), b0), dense(r0, L, N), level, (i64)galois);
+    LAUNCH(k_automorphism, gridb, dim3(256), st, c->dev(), shift(view(c1), b0), dense(r1, L, N), level, (i64)galois);
+    rc = keyswitch_chunk(c, level, nb, dense(r1, L, N), key, dense(r0, L, N), dense(r0, L, N), shift(view(out0), b0),
+                         shift(view(out1), b0), 2, ksws, st);
+    if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+// forward transforms + tensor product of one chunk; x: 4 polys [4][nb][L][N] workspace (x0,x1,y0,y1)
+static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbView b0, TbView b1, int pre_rescale,
+                      i64* x, TbView d0, TbView d1, TbView d2, tb200_stream st) {
+  const int N = c->N;
+  const int lvl = level + (pre_rescale ? 1 : 0);
+  const int L = c->num_ord - lvl;
+  const size_t pe = (size_t)nb * L * N;
+  TbView in[4] = {a0, a1, b0, b1};
+  for (int i = 0; i < 4; ++i) {
+    TbView xi = dense(x + i * pe, L, N);
+    if (pre_rescale) {
+      rescale_impl(c, level, nb, in[i], xi, 1, st);
+      int rc = ntt_forward(c, xi, xi, L, nb, lvl, true, st);
+      if (rc) return rc;
+    } else {
+      int rc = ntt_forward(c, in[i], xi, L, nb, lvl, true, st);
+      if (rc) return rc;
+    }
+  }
+  LAUNCH(k_tensor, grid_pw(c, L, nb, 2), dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), dense(x, L, N),
+         dense(x + pe, L, N), dense(x + 2 * pe, L, N), dense(x + 3 * pe, L, N), d0, d1, d2, lvl, N);
+  return 0;
+}
+
+extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,
+                                     const tb200_poly* b0, const tb200_poly* b1, const tb200_poly* d0,
+                                     const tb200_poly* d1, const tb200_poly* d2, int pre_rescale, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (pre_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "cc_mult: no level left to rescale");
+  CHECK_POLY(a0);
+  CHECK_POLY(a1);
+  CHECK_POLY(b0);
+  CHECK_POLY(b1);
+  CHECK_POLY(d0);
+  CHECK_POLY(d1);
+  CHECK_POLY(d2);
+  CK(cudaSetDevice(c->device));
+  const int lvl = level + (pre_rescale ? 1 : 0), L = c->num_ord - lvl;
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  if ((rc = ws_reserve(c, 4 * (size_t)ch * L * c->N))) return rc;
+  for (int b = 0; b < batch; b += ch) {
+    const int nb = batch - b < ch ? batch - b : ch;
+    rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
+                    pre_rescale, c->ws, shift(view(d0), b), shift(view(d1), b), shift(view(d2), b), st);
+    if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+// relinearize one chunk: d (dense [3][nb][L][N], NTT+Montgomery, destroyed) -> out
+static int relin_chunk(tb200_ctx* c, int lvl, int nb, i64* d, const TbKskDev& key, TbView out0, TbView out1, i64* ksws,
+                       tb200_stream st) {
+  const int N = c->N, L = c->num_ord - lvl;
+  const size_t pe = (size_t)nb * L * N;
+  int rc = ntt_inverse(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, 2, st);
+  if (rc) return rc;
+  return keyswitch_chunk(c, lvl, nb, dense(d + 2 * pe, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1, 1,
+                         ksws, st);
+}
+
+extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200_poly* d0, const tb200_poly* d1,
+                                 const tb200_poly* d2, const tb200_ksk* evk, const tb200_poly* out0,
+                                 const tb200_poly* out1, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  CHECK_POLY(d0);
+  CHECK_POLY(d1);
+  CHECK_POLY(d2);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  TbKskDev key;
+  if ((rc = make_key(c, level, evk, &key))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int N = c->N, L = c->num_ord - level;
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  if ((rc = ws_reserve(c, (3 * (size_t)L * N + ks_ws_elems(c, level)) * ch))) return rc;
+  for (int b = 0; b < batch; b += ch) {
+    const int nb = batch - b < ch ? batch - b : ch;
+    const size_t pe = (size_t)nb * L * N;
+    i64* d = c->ws;
+    const tb200_poly* src[3] = {d0, d1, d2};
+    for (int i = 0; i < 3; ++i) {  // copy (the reference mutates its triplet; we do not)
+      TbPwArgs g;
+      memset(&g, 0, sizeof(g));
+      g.a = shift(view(src[i]), b);
+      g.b = g.a;
+      g.out = dense(d + i * pe, L, N);
+      g.prime0 = level;
+      g.N = N;
+      launch_pw<15>(c, g, L, nb, st);
+    }
+    rc = relin_chunk(c, level, nb, d, key, shift(view(out0), b), shift(view(out1), b), d + 3 * pe, st);
+    if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_cc_mult_relin(tb200_ctx* c, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,
+                                   const tb200_poly* b0, const tb200_poly* b1, const tb200_ksk* evk,
+                                   const tb200_poly* out0, const tb200_poly* out1, int pre_rescale, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (pre_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "cc_mult: no level left to rescale");
+  CHECK_POLY(a0);
+  CHECK_POLY(a1);
+  CHECK_POLY(b0);
+  CHECK_POLY(b1);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  const int lvl = level + (pre_rescale ? 1 : 0);
+  TbKskDev key;
+  if ((rc = make_key(c, lvl, evk, &key))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int N = c->N, L = c->num_ord - lvl;
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  // workspace: x[4] | d[3] | key-switch
+  if ((rc = ws_reserve(c, (7 * (size_t)L * N + ks_ws_elems(c, lvl)) * ch))) return rc;
+  for (int b = 0; b < batch; b += ch) {
+    const int nb = batch - b < ch ? batch - b : ch;
+    const size_t pe = (size_t)nb * L * N;
+    i64* x = c->ws;
+    i64* d = x + 4 * pe;
+    i64* ksws = d + 3 * pe;
+    rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
+                    pre_rescale, x, dense(d, L, N), dense(d + pe, L, N), dense(d + 2 * pe, L, N), st);
+    if (rc) return rc;
+    rc = relin_chunk(c, lvl, nb, d, key, shift(view(out0), b), shift(view(out1), b), ksws, st);
+    if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_pc_mult(tb200_ctx* c, int level, int batch, const tb200_poly* pt, const tb200_poly* c0,
+                             const tb200_poly* c1, const tb200_poly* out0, const tb200_poly* out1, int post_rescale,
+                             tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (post_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "pc_mult: no level left to rescale");
+  CHECK_POLY(pt);
+  CHECK_POLY(c0);
+  CHECK_POLY(c1);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  CK(cudaSetDevice(c->device));
+  const int N = c->N, L = c->num_ord - level;
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  if ((rc = ws_reserve(c, 2 * (size_t)ch * L * N))) return rc;
+  for (int b = 0; b < batch; b += ch) {
+    const int nb = batch - b < ch ? batch - b : ch;
+    const size_t pe = (size_t)nb * L * N;
+    const tb200_poly* in[2] = {c0, c1};
+    const tb200_poly* out[2] = {out0, out1};
+    for (int h = 0; h < 2; ++h) {
+      TbView x = dense(c->ws + h * pe, L, N);
+      if ((rc = ntt_forward(c, shift(view(in[h]), b), x, L, nb, level, true, st))) return rc;
+      TbPwArgs g;
+      memset(&g, 0, sizeof(g));
+      TbView ptv = view(pt);
+      if (ptv.bs != 0) ptv = shift(ptv, b);
+      g.a = ptv;  // mont_mult(pt_, ct): pt is the first operand (ckks_engine.py:2569)
+      g.b = x;
+      g.out = x;
+      g.prime0 = level;
+      g.N = N;
+      launch_pw<0>(c, g, L, nb, st);
+      TbView dst = post_rescale ? x : shift(view(out[h]), b);
+      if ((rc = ntt_inverse(c, x, dst, L, nb, level, 2, st))) return rc;
+      if (post_rescale) rescale_impl(c, level, nb, x, shift(view(out[h]), b), 1, st);
+    }
+  }
+  POST();
+  return 0;
+}
+
+extern "C" int tb200_cc_addsub(tb200_ctx* c, int level, int batch, int sub, const tb200_poly* a0, const tb200_poly* a1,
+                               const tb200_poly* b0, const tb200_poly* b1, const tb200_poly* out0,
+                               const tb200_poly* out1, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  CHECK_POLY(a0);
+  CHECK_POLY(a1);
+  CHECK_POLY(b0);
+  CHECK_POLY(b1);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  CK(cudaSetDevice(c->device));
+  const int L = c->num_ord - level;
+  const tb200_poly* A[2] = {a0, a1};
+  const tb200_poly* B[2] = {b0, b1};
+  const tb200_poly* O[2] = {out0, out1};
+  for (int h = 0; h < 2; ++h) {
+    TbPwArgs g;
+    memset(&g, 0, sizeof(g));
+    g.a = view(A[h]);
+    g.b = view(B[h]);
+    g.out = view(O[h]);
+    g.prime0 = level;
+    g.N = c->N;
+    if (sub)
+      launch_pw<4>(c, g, L, batch, st);
+    else
+      launch_pw<3>(c, g, L, batch, st);
+  }
+  POST();
+  return 0;
+}

@@ -1,0 +1,85 @@
+// tb200_ctx.h -- host side of the context: every prime-dependent constant the kernels consume.
+//
+// Restates (in C++ with 128-bit integers) what the reference derives in Python:
+//   tiberate/context/mont_context.py:26-57        R = 2^62, R^2 mod q, k = (R R^-1 - 1)/q
+//   tiberate/context/ntt_context.py:21-85,277-298 psi root (smallest x >= 2 rule), power tables in
+//                                                 bit-reversed order, twiddles entered into
+//                                                 Montgomery form with mont_enter_Rs (lazy), N^-1 R
+//   tiberate/context/rns_partition.py:7-66        digit groups (single device; limb sharding is
+//                                                 layered on top by the host, see dist.py)
+//   tiberate/context/ntt_context.py:497-534       Y_scalar / L_scalar / L_enter
+//   tiberate/ckks_engine.py:114-143,201-239       rescale scales, P_k^-1 R tables
+#pragma once
+#include <string>
+#include <vector>
+
+#include "tb200_kernels.cuh"
+
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+
+static inline u64 h_mulmod(u64 a, u64 b, u64 m) { return (u64)((u128)a * b % m); }
+static inline u64 h_powmod(u64 a, u64 e, u64 m) {
+  u64 r = 1 % m;
+  a %= m;
+  while (e) {
+    if (e & 1) r = h_mulmod(r, a, m);
+    a = h_mulmod(a, a, m);
+    e >>= 1;
+  }
+  return r;
+}
+static inline u64 h_invmod_prime(u64 a, u64 p) { return h_powmod(a % p, p - 2, p); }
+// -q^-1 mod 2^62 by Newton iteration (q odd)
+static inline u64 h_neg_inv_pow2(u64 q) {
+  u64 x = q;  // correct to 3 bits
+  for (int i = 0; i < 6; ++i) x *= 2 - q * x;
+  return (0 - x) & TB_MASK62;
+}
+// host copy of the exact Montgomery product (same closed form as tb_mm_ss)
+static inline i64 h_mm(i64 a, i64 b, i64 q, u64 k) {
+  const i128 x = (i128)a * (i128)b;
+  const u64 s = ((u64)x * k) & TB_MASK62;
+  const i128 t = x + (i128)((u128)s * (u128)(u64)q);
+  return (i64)(t >> 62);
+}
+static inline int h_bitrev(int x, int bits) {
+  int r = 0;
+  for (int i = 0; i < bits; ++i) {
+    r = (r << 1) | (x & 1);
+    x >>= 1;
+  }
+  return r;
+}
+
+struct tb200_ctx {
+  int device = 0, logN = 0, N = 0, P = 0, K = 0, LA = 0, LB = 0, scale_bits = 40, num_ord = 0;
+  int num_levels = 0;  // levels 0..num_ord-1 (level = number of dropped scale primes)
+  int chunk = 4;
+  std::vector<i64> q;
+  std::vector<u64> k;
+  std::vector<TbPrime> primes;
+  std::vector<u64> psi, ipsi;  // [P][N] lazy Montgomery twiddles (unshifted), host copies
+  std::vector<TbKsLevel> ks;   // per level
+  // device
+  TbPrime* d_primes = nullptr;
+  u64 *d_psi4 = nullptr, *d_ipsi4 = nullptr;
+  i64* d_rescale = nullptr;  // [num_ord][P]: row l, column g = (q_l^-1 mod q_g) R mod q_g
+  i64* d_pir = nullptr;      // [K][P]
+  i64* d_pir_sp = nullptr;   // [K][K]  (k, row)
+  i64* d_lenter = nullptr;   // all groups' L_enter blocks
+  TbKsLevel* d_ks = nullptr; // [num_ord]
+  i64* ws = nullptr;         // engine workspace
+  size_t ws_elems = 0;
+  TbDev dev() const {
+    TbDev d;
+    d.pr = d_primes;
+    d.psi4 = d_psi4;
+    d.ipsi4 = d_ipsi4;
+    d.logN = logN;
+    d.LA = LA;
+    d.LB = LB;
+    d.P = P;
+    return d;
+  }
+};

@@ -1,0 +1,93 @@
+// tb200_platform.h -- CUDA build glue.
+//
+// The product is compiled by nvcc for sm_100a only.  The same kernel sources can additionally be
+// compiled by g++ with -DTB200_HOST_EMU for tests/emu (a thread-per-CUDA-thread interpreter that
+// lets the indexing logic of the kernels be checked against the oracle in a container without a
+// GPU).  That build is test infrastructure: the product loader never loads it and there is no
+// CPU fallback in the product path.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+
+#ifndef TB200_HOST_EMU
+// ------------------------------------------------------------------ real CUDA
+#include <cuda_runtime.h>
+#define TB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define TB_KERNEL_SHARED __shared__
+#else
+// ------------------------------------------------------------------ host emulation (tests only)
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct emu_uint3 {
+  unsigned x, y, z;
+};
+extern thread_local emu_uint3 threadIdx;
+extern thread_local emu_uint3 blockIdx;
+extern thread_local dim3 blockDim;
+extern thread_local dim3 gridDim;
+void emu_syncthreads();
+void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body);
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define TB_KERNEL_SHARED static
+#define __syncthreads() emu_syncthreads()
+template <class T>
+static inline T __ldg(const T* p) {
+  return *p;
+}
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+  return (unsigned long long)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+}
+static inline long long __mul64hi(long long a, long long b) {
+  return (long long)(((__int128)a * (__int128)b) >> 64);
+}
+struct alignas(16) longlong2 {
+  long long x, y;
+};
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = std::malloc(n ? n : 1);
+  return *p ? 0 : 2;
+}
+static inline cudaError_t cudaFree(void* p) {
+  std::free(p);
+  return 0;
+}
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) {
+  std::memcpy(d, s, n);
+  return 0;
+}
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  std::memcpy(d, s, n);
+  return 0;
+}
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
+  std::memset(d, v, n);
+  return 0;
+}
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaGetDevice(int* d) {
+  *d = 0;
+  return 0;
+}
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaPeekAtLastError() { return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaDeviceSynchronize() { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+#define TB_LAUNCH(kernel, grid, block, stream, ...) \
+  emu_launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#endif
