@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- HMult+relin (cc_mult with pre-rescale and relinearisation) throughput at logN=16.
+
+Workload (BASELINE.json configs[2]): the reference's logN16 preset (N=65536, 34 scale + 1 base + 4
+special primes, 10 digit groups), a batch of synthetic ciphertext pairs at level 0, one "step" =
+one batched cc_mult+relin over the whole per-GPU batch.  Ranks shard by ciphertext batch (no
+collective on the data path, scaling "weak": the per-GPU batch is fixed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LOGN = 16
+METRIC = "HMult+relin ops/s at logN=16"
+UNIT = "ops/s"
+
+
+def preset():
+    from tiberate_fhe_b200.presets import PRESETS
+
+    return PRESETS[LOGN]["q"], PRESETS[LOGN]["K"]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_hmult(steps: int, warmup: int):
+    """The oracle port (NumPy + C/OpenMP, oracle/) timed on the host cores: one HMult+relin of one
+    logN16 ciphertext pair per step.  The only place bench.py executes oracle/ code."""
+    import numpy as np
+
+    import oracle
+    from oracle.context import OracleContext
+    from oracle.engine import OracleEngine
+
+    oracle.build()
+    q, K = preset()
+    octx = OracleContext(LOGN, q, K)
+    eng = OracleEngine(octx)
+    rng = np.random.default_rng(0xB200)
+    lp = octx.level_primes(0, False)
+    allp = list(range(octx.P))
+    evk = [(eng.uniform(rng, allp), eng.uniform(rng, allp)) for _ in range(octx.part.num_partitions + 1)]
+    a = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+    b = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+    for _ in range(warmup):
+        eng.cc_mult(a, b, evk, 0)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        eng.cc_mult(a, b, evk, 0)
+        times.append(time.perf_counter() - t0)
+    return times, os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, cores = cpu_oracle_hmult(args.steps, min(args.warmup, 1))
+    total = sum(times)
+    value = len(times) / total
+    sample = f"{len(times)} x 1 HMult+relin of one logN16 ciphertext pair (L=34, K=4, 10 digit groups), oracle port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "logN16 preset, level 0, cc_mult(pre_rescale)+relinearize, 1 ciphertext pair per step",
+                   "note": "the reference has no CPU path (GPU-only); this arm times the CPU oracle port of its "
+                           "algorithm on the host cores (NumPy + C/OpenMP)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from tiberate_fhe_b200 import KeySwitchKeyView, Tb200Context, galois_element, get_lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = get_lib()
+    q, K = preset()
+    ctx = Tb200Context(LOGN, q, K, device=local)
+    ctx.set_chunk(args.chunk)
+    N, P, no = ctx.N, ctx.P, ctx.num_ordinary
+    L = no - 1
+    B = args.batch
+    gen = torch.Generator(device=dev).manual_seed(0xB200 + rank)
+
+    def uniform(shape_rows, primes):
+        t = torch.empty(*shape_rows, dtype=torch.int64, device=dev)
+        for i, qi in enumerate(primes):
+            t[..., i, :].random_(0, int(qi), generator=gen)
+        return t
+
+    a0, a1, b0, b1 = (uniform((B, no, N), q[:no]) for _ in range(4))
+    ng = ctx.num_groups0
+    evk = KeySwitchKeyView([(uniform((P, N), q), uniform((P, N), q)) for _ in range(ng)], N)
+    rotk = KeySwitchKeyView([(uniform((P, N), q), uniform((P, N), q)) for _ in range(ng)], N)
+    out0 = torch.empty(B, L, N, dtype=torch.int64, device=dev)
+    out1 = torch.empty(B, L, N, dtype=torch.int64, device=dev)
+    g1 = galois_element(N, 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def hmult():
+        ctx.cc_mult_relin(0, a0, a1, b0, b1, evk, out0, out1, True)
+
+    sampler = ClockSampler(local)
+    launches0 = lib.tb200_launch_count()
+    if rank == 0:
+        sampler.start()
+    ms = timed(hmult, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (lib.tb200_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- secondary figures of the BASELINE metric: rotate ops/s and (i)NTT Glimb/s -----------------
+    extra = {}
+    if not args.quick:
+        r0 = torch.empty(B, no, N, dtype=torch.int64, device=dev)
+        r1 = torch.empty(B, no, N, dtype=torch.int64, device=dev)
+        k2 = max(2, args.steps // 2)
+        ms_rot = timed(lambda: ctx.rotate(0, g1, a0, a1, rotk, r0, r1), k2, 1)
+        extra["rotate_ops_per_s"] = world * B * k2 / (ms_rot / 1e3)
+        r0.copy_(a0)
+        ms_f = timed(lambda: ctx.ntt(r0, 0, True), k2, 1)
+        ms_i = timed(lambda: ctx.intt(r0, 0, 2), k2, 1)
+        extra["ntt_fwd_glimbs_per_s"] = world * B * no * N * k2 / (ms_f / 1e3) / 1e9
+        extra["ntt_inv_glimbs_per_s"] = world * B * no * N * k2 / (ms_i / 1e3) / 1e9
+        extra["ntt_hbm_roofline_glimbs_per_s"] = measured_peaks()[0] / 16.0
+        ms_rs = timed(lambda: ctx.rescale(0, a0, a1, out0, out1), k2, 1)
+        extra["rescale_ops_per_s"] = world * B * k2 / (ms_rs / 1e3)
+        del r0, r1
+
+    # ---- per-kernel time inside the step (CUDA events around every launch, separate pass) ----------
+    lib.tb200_prof_enable(1)
+    psteps = 1
+    for _ in range(psteps):
+        hmult()
+    import ctypes
+
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.tb200_prof_collect(buf, len(buf))
+    lib.tb200_prof_enable(0)
+    kern = {}
+    for ln in buf.value.decode().splitlines():
+        name, cnt, tot = ln.split("\t")
+        kern[name] = (int(cnt), float(tot))
+    tot_ms = sum(v[1] for v in kern.values()) or 1.0
+    shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])}
+    top = max(kern, key=lambda k_: kern[k_][1]) if kern else None
+    peak, peak_src = measured_peaks()
+    # limbs transformed per HMult by each NTT pass kernel (DESIGN.md "Kernels"): forward passes see
+    # 4 L (inputs) + ngroups (L+K) (ModUp) limbs, inverse passes 3 L + 2 (L+K); 16 B per residue.
+    E = L + K
+    limbs = {"k_ntt_fwd_A": 4 * L + ng * E, "k_ntt_fwd_B": 4 * L + ng * E, "k_ntt_inv_A": 3 * L + 2 * E,
+             "k_ntt_inv_B": 3 * L + 2 * E}
+    roof = None
+    if top in limbs:
+        nl, tms = kern[top]
+        bytes_per_launch = B * limbs[top] * N * 16.0 * psteps / nl
+        ach = bytes_per_launch / (tms / nl / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": tms / nl, "launches_per_step": nl // psteps,
+                "note": "read+write of every residue once (16 B) per pass; kernel is INT-pipe bound, see DESIGN.md"}
+    elif top is not None:
+        nl, tms = kern[top]
+        roof = {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": tms / nl}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if roof and os.path.exists(tpath):
+        with open(tpath) as f:
+            roof["traffic"] = json.load(f).get(roof["kernel"])
+
+    # ---- end to end: host (pinned) buffers -> C ABI -> host result, copies inside the timed region --
+    Be = min(B, args.e2e_batch)
+    hin = [torch.empty(Be, no, N, dtype=torch.int64).pin_memory() for _ in range(4)]
+    for hbuf, src in zip(hin, (a0, a1, b0, b1)):
+        hbuf.copy_(src[:Be])
+    hout = [torch.empty(Be, L, N, dtype=torch.int64).pin_memory() for _ in range(2)]
+    din = [t[:Be] for t in (a0, a1, b0, b1)]
+    dout = [out0[:Be], out1[:Be]]
+
+    def e2e_step():
+        for d, h_ in zip(din, hin):
+            d.copy_(h_, non_blocking=True)
+        ctx.cc_mult_relin(0, din[0], din[1], din[2], din[3], evk, dout[0], dout[1], True)
+        for h_, d in zip(hout, dout):
+            h_.copy_(d, non_blocking=True)
+
+    ms_e2e = timed(e2e_step, args.steps, 1)
+    e2e = {"value": world * Be * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": 4 * Be * no * N * 8, "d2h_bytes_per_step": 2 * Be * L * N * 8,
+           "batch": Be, "ms_per_step": ms_e2e / args.steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_oracle_hmult(2, 1)
+        cpu = {"value": 1.0 / min(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "best of 2 x 1 HMult+relin of one logN16 ciphertext pair (oracle port, NumPy + C/OpenMP)"}
+
+    if rank == 0:
+        alg_bytes = (6 * L + 4 + 2 * ng * E) * N * 8  # SURVEY.md 8(d), un-amortised
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "logN16 preset (N=65536, 35 ordinary + 4 special primes, 10 digit groups), level 0, "
+                                   "cc_mult(pre_rescale)+relinearize", "batch_per_gpu": B, "chunk": args.chunk,
+                       "sharding": "ciphertext batch, no data-path collective",
+                       "l2": "inputs (>= 17 GiB per step at batch 256) exceed the 126 MB L2"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "cpu_baseline": cpu, "kernel_time_share": shares,
+            "hmult_hbm_roofline": {"algorithmic_bytes_per_op": alg_bytes, "roofline_ops_per_s": peak * 1e9 / alg_bytes,
+                                   "frac": value / world / (peak * 1e9 / alg_bytes)},
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--chunk", type=int, default=4, help="ciphertexts per internal pass (workspace size)")
+    ap.add_argument("--e2e-batch", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="skip the secondary rotate / NTT figures")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

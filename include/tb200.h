@@ -168,6 +168,10 @@ int tb200_cc_addsub(tb200_ctx*, int level, int batch, int sub, const tb200_poly*
 
 /* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
 int64_t tb200_launch_count(void);
+/* per-kernel timing for bench.py's roofline: while enabled every launch is bracketed by CUDA events;
+ * collect() synchronises and writes "kernel\tlaunches\ttotal_ms\n" lines (returns bytes written). */
+void tb200_prof_enable(int on);
+int tb200_prof_collect(char* buf, int cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,87 @@
+"""Kernel sources compiled for the host (tests/emu) vs the oracle, bit-exact, on small rings.
+
+This exercises the real kernel code (tile NTT index maps, twiddle addressing, digit/extend/ModDown
+tables, launch geometry, workspace layout) in a container without a GPU.  It is NOT a product path:
+the product only ever loads the CUDA build (tiberate_fhe_b200/_native.py).  The GPU parity tests
+proper are tests/test_gpu_parity.py (-m gpu).
+"""
+
+import pytest
+
+import parity
+from parity import Harness, Setup
+
+
+@pytest.fixture(scope="module")
+def h(emu_lib):
+    return Harness(emu_lib, use_torch=False)
+
+
+# (logN, num_scales, K): covers LA/LB = 4/4, 5/4, 5/5, 6/5, 4/8 and every tile-round pattern
+CASES = [(8, 5, 2), (9, 4, 3), (10, 3, 1), (11, 6, 4), (12, 2, 2)]
+
+
+@pytest.mark.parametrize("logN,ns,K", CASES)
+def test_context_and_ntt(h, logN, ns, K):
+    s = Setup.toy(h, logN, ns, K, seed=logN)
+    try:
+        parity.check_context(s)
+        parity.check_ntt(s, level=0, with_special=True, batch=2)
+        parity.check_ntt(s, level=min(1, ns), with_special=False, batch=1)
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("logN,ns,K", [(8, 5, 2), (10, 3, 1)])
+def test_pointwise_and_he_ops(h, logN, ns, K):
+    s = Setup.toy(h, logN, ns, K, seed=100 + logN)
+    try:
+        parity.check_pointwise(s, level=0, with_special=True)
+        parity.check_pointwise(s, level=1, with_special=False)
+        for level in range(0, ns + 1):
+            parity.check_he_ops(s, level)
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("logN,ns,K", [(8, 5, 2), (9, 4, 3), (10, 3, 1)])
+def test_engine_every_level(h, logN, ns, K):
+    s = Setup.toy(h, logN, ns, K, seed=200 + logN, rot_deltas=(1, 3))
+    try:
+        for level in range(0, ns + 1):
+            parity.check_engine(s, level)
+    finally:
+        s.close()
+
+
+def test_engine_batched_and_chunked(h):
+    s = Setup.toy(h, 8, 4, 2, seed=7)
+    try:
+        s.ctx.set_chunk(2)  # batch 3 -> chunks of 2 + 1
+        parity.check_engine(s, 0, batch=3)
+        parity.check_engine(s, 2, batch=3, ops=("keyswitch", "rotate", "cc_mult", "pc_mult"))
+    finally:
+        s.close()
+
+
+def test_bad_arguments_raise(h):
+    import numpy as np
+
+    from tiberate_fhe_b200 import Tb200Error
+    from tiberate_fhe_b200.context import Tb200Context
+
+    with pytest.raises(Tb200Error):
+        Tb200Context(8, [17, 19, 23], 1, lib=h.lib)  # not NTT friendly
+    s = Setup.toy(h, 8, 3, 1, seed=1)
+    try:
+        a = np.zeros((4, s.N), dtype=np.int64)
+        with pytest.raises(Tb200Error):
+            s.ctx.ntt(a, s.octx.P - 2, True)  # rows run past the last prime
+        with pytest.raises(Tb200Error):
+            s.ctx.ntt(np.zeros((4, s.N), dtype=np.int32), 0, True)  # wrong dtype
+        with pytest.raises(Tb200Error):
+            s.ctx.rescale(s.octx.num_ordinary - 1, a[:1], a[:1], a[:1], a[:1])  # no level left
+        with pytest.raises(Tb200Error):
+            s.ctx.rotate(0, 4, a, a, None, a.copy(), a.copy())  # even galois element
+    finally:
+        s.close()

@@ -66,6 +66,8 @@ SIGNATURES = {
     "tb200_pc_mult": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_addsub": (_i, [_vp, _i, _i, _i, PP, PP, PP, PP, PP, PP, _vp]),
     "tb200_launch_count": (_i64, []),
+    "tb200_prof_enable": (None, [_i]),
+    "tb200_prof_collect": (_i, [C.c_char_p, _i]),
 }
 
 

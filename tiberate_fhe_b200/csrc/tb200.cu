@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <vector>
 
 #include "../../include/tb200.h"
 #include "tb200_ctx.h"
@@ -21,10 +22,41 @@ static int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (call);                                                             \
     if (e_ != cudaSuccess) return fail((int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
-#define LAUNCH(kernel, grid, block, stream, ...)               \
-  do {                                                         \
+// Optional per-kernel timing (bench.py roofline): when enabled every launch is bracketed by CUDA
+// events on the launching stream; tb200_prof_collect() later sums the elapsed time per kernel name.
+struct ProfRec {
+  const char* name;
+#ifndef TB200_HOST_EMU
+  cudaEvent_t e0, e1;
+#endif
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+#ifndef TB200_HOST_EMU
+#define PROF_BEGIN(name_, stream)                                 \
+  ProfRec pr_;                                                    \
+  if (g_prof_on) {                                                \
+    pr_.name = name_;                                             \
+    cudaEventCreate(&pr_.e0);                                     \
+    cudaEventCreate(&pr_.e1);                                     \
+    cudaEventRecord(pr_.e0, (cudaStream_t)(stream));              \
+  }
+#define PROF_END(stream)                             \
+  if (g_prof_on) {                                   \
+    cudaEventRecord(pr_.e1, (cudaStream_t)(stream)); \
+    g_prof.push_back(pr_);                           \
+  }
+#else
+#define PROF_BEGIN(name_, stream)
+#define PROF_END(stream)
+#endif
+#define LAUNCH(kernel, grid, block, stream, ...) LAUNCHN(#kernel, kernel, grid, block, stream, __VA_ARGS__)
+#define LAUNCHN(kname, kernel, grid, block, stream, ...)                 \
+  do {                                                                   \
+    PROF_BEGIN(kname, stream)                                            \
     TB_LAUNCH(kernel, grid, block, (cudaStream_t)(stream), __VA_ARGS__); \
-    g_launches.fetch_add(1, std::memory_order_relaxed);        \
+    PROF_END(stream)                                                     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                  \
   } while (0)
 #define POST()                                                                     \
   do {                                                                             \
@@ -35,6 +67,41 @@ static int fail(int code, const char* fmt, ...) {
 extern "C" const char* tb200_last_error(void) { return g_err; }
 extern "C" const char* tb200_version(void) { return "tb200 0.1 (sm_100a)"; }
 extern "C" int64_t tb200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" void tb200_prof_enable(int on) {
+  g_prof_on = on != 0;
+}
+// Synchronises, then writes "name\tlaunches\ttotal_ms\n" lines into buf; returns bytes written.
+extern "C" int tb200_prof_collect(char* buf, int cap) {
+  int n = 0;
+#ifndef TB200_HOST_EMU
+  cudaDeviceSynchronize();
+  std::vector<const char*> names;
+  std::vector<double> ms;
+  std::vector<long> cnt;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    size_t i = 0;
+    for (; i < names.size(); ++i)
+      if (strcmp(names[i], r.name) == 0) break;
+    if (i == names.size()) {
+      names.push_back(r.name);
+      ms.push_back(0);
+      cnt.push_back(0);
+    }
+    ms[i] += t;
+    cnt[i] += 1;
+  }
+  for (size_t i = 0; i < names.size() && n < cap - 128; ++i)
+    n += snprintf(buf + n, cap - n, "%s\t%ld\t%.6f\n", names[i], cnt[i], ms[i]);
+#endif
+  g_prof.clear();
+  if (cap > 0) buf[n < cap ? n : cap - 1] = 0;
+  return n;
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -297,7 +364,8 @@ static inline dim3 grid_pw(const tb200_ctx* c, int rows, int batch, int per_thre
 template <int OP>
 static void launch_pw(const tb200_ctx* c, const TbPwArgs& a, int rows, int batch, tb200_stream st) {
   auto kfn = k_pointwise<OP>;
-  LAUNCH(kfn, grid_pw(c, rows, batch, 2), dim3(c->N / 2 < 256 ? c->N / 2 : 256), st, c->dev(), a);
+  LAUNCHN(OP == 0 ? "k_pointwise<mult>" : (OP == 15 ? "k_pointwise<copy>" : "k_pointwise<other>"), kfn,
+          grid_pw(c, rows, batch, 2), dim3(c->N / 2 < 256 ? c->N / 2 : 256), st, c->dev(), a);
 }
 
 extern "C" int tb200_pointwise(tb200_ctx* c, int op, int rows, int batch, int prime0, const tb200_poly* a,
@@ -375,7 +443,7 @@ static int launch_fwd_A(const tb200_ctx* c, TbView src, TbView dst, int rows, in
 #define ACASE(n)                                            \
   case n: {                                                 \
     auto kfn = k_ntt_fwd_A<n, PRO>;                         \
-    LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
+    LAUNCHN("k_ntt_fwd_A", kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
   } break;
     ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
 #undef ACASE
@@ -392,7 +460,7 @@ static int launch_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, in
 #define ACASE(n)                                            \
   case n: {                                                 \
     auto kfn = k_ntt_inv_A<n, EPI>;                         \
-    LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
+    LAUNCHN("k_ntt_inv_A", kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
   } break;
     ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
 #undef ACASE
@@ -410,10 +478,10 @@ static int launch_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, in
   case n: {                                                      \
     if (inverse) {                                               \
       auto kfn = k_ntt_inv_B<n>;                                 \
-      LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0);  \
+      LAUNCHN("k_ntt_inv_B", kfn, grid, block, st, c->dev(), src, dst, prime0);  \
     } else {                                                     \
       auto kfn = k_ntt_fwd_B<n>;                                 \
-      LAUNCH(kfn, grid, block, st, c->dev(), src, dst, prime0);  \
+      LAUNCHN("k_ntt_fwd_B", kfn, grid, block, st, c->dev(), src, dst, prime0);  \
     }                                                            \
   } break;
     BCASE(4) BCASE(5) BCASE(6) BCASE(7) BCASE(8)
