@@ -1,0 +1,103 @@
+"""Drop-in check (BASELINE.json configs[1]): the UNMODIFIED reference CkksEngine (pip-installed
+under baseline/_ref with its own CUDA extension) runs its README scenario twice from the same CSPRNG
+state -- once on its own operators, once with tiberate_fhe_b200 installed behind
+tiberate.libs.wrapper -- and every integer tensor (keys, ciphertexts after encodecrypt, pc_mult,
+pc_add, cc_mult+relin, rescale, cc_add, rotate_single) must be bit-identical; decrypted values too.
+Skipped when baseline/_ref is absent (it is git-ignored; `pip install --target baseline/_ref` +
+`python baseline/ref_harness.py`).
+"""
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _flatten(x, out):
+    import torch
+
+    if isinstance(x, torch.Tensor):
+        out.append(x.detach().clone())
+    elif isinstance(x, (list, tuple)):
+        for y in x:
+            _flatten(y, out)
+    elif hasattr(x, "data") and not isinstance(x, (int, float, str)):
+        _flatten(x.data, out)
+    return out
+
+
+@pytest.mark.parametrize("preset", ["logN14", "logN15"])
+def test_reference_engine_on_tb200_backend_is_bit_identical(preset):
+    import torch
+
+    from baseline import ref_harness
+
+    if not ref_harness.available():
+        pytest.skip("baseline/_ref (reference install) not present")
+    ref_harness.load()
+    from tiberate import CkksEngine, Preset
+    from tiberate.typing import Plaintext
+
+    from tiberate_fhe_b200 import backend, get_lib
+
+    engine = CkksEngine(getattr(Preset, preset), devices=["cuda:0"])
+    states0 = [s.clone() for s in engine.rng.states]
+    gen = torch.Generator().manual_seed(1234)
+    data = torch.randn(engine.num_slots, generator=gen, dtype=torch.float64)
+
+    def scenario():
+        for s, s0 in zip(engine.rng.states, states0):
+            s.copy_(s0)
+        for name in ("sk", "pk", "evk", "gk"):
+            setattr(engine, f"_CkksEngine__{name}", None)
+        engine._CkksEngine__rotk = {}
+        rec = {}
+        rec["sk"] = engine.sk
+        rec["pk"] = engine.pk
+        rec["evk"] = engine.evk
+        rotk1 = engine.rotk[1]
+        rec["rotk1"] = rotk1
+        ct = engine.encodecrypt(data)
+        rec["encodecrypt"] = ct.clone()
+        pt = Plaintext(data)
+        ct2 = engine.pc_mult(pt, ct)
+        rec["pc_mult"] = ct2.clone()
+        ct3 = engine.pc_add(pt, ct2)
+        rec["pc_add"] = ct3.clone()
+        ct4 = engine.cc_mult(ct3, ct3)
+        rec["cc_mult_relin"] = ct4.clone()
+        rec["rescale"] = engine.rescale(ct4).clone()
+        ct5 = engine.cc_add(ct4, ct4)
+        rec["cc_add"] = ct5.clone()
+        ct6 = engine.rotate_single(ct5, rotk1)
+        rec["rotate_single"] = ct6.clone()
+        rec["triplet"] = engine.cc_mult(ct6, ct6, post_relin=False).clone()
+        dec = engine.decryptcode(ct6, is_real=True)
+        torch.cuda.synchronize()
+        return {k: _flatten(v, []) for k, v in rec.items()}, dec.detach().cpu().clone()
+
+    ref_out, ref_dec = scenario()
+    lib = get_lib()
+    before = lib.tb200_launch_count()
+    backend.install_as_tiberate_backend(engine)
+    try:
+        our_out, our_dec = scenario()
+    finally:
+        backend.uninstall()
+    assert lib.tb200_launch_count() - before > 100, "the tb200 operators were not used"
+    for name in ref_out:
+        a, b = ref_out[name], our_out[name]
+        assert len(a) == len(b) and len(a) > 0, name
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert x.shape == y.shape, (name, i)
+            if not torch.equal(x, y):
+                bad = (x != y).nonzero()
+                raise AssertionError(f"{name}[{i}]: {bad.shape[0]} residues differ, first at {bad[0].tolist()}: "
+                                     f"reference {x[tuple(bad[0])].item()} ours {y[tuple(bad[0])].item()}")
+    assert torch.equal(ref_dec, our_dec), "decrypted values differ"
+    # and the decrypted result is the expected function of the data within the reference's error bars
+    want = data * data + data
+    want = want * want
+    want = want + want
+    want = torch.roll(want, -1)  # rotk[1] rotates by one slot
+    err = (ref_dec[: data.numel()].double() - want).abs().max().item()
+    assert err < 1e-2, err

@@ -1,0 +1,120 @@
+"""Layout-compatible data structures for the hot path (mirror of tiberate/typing.py:24-49 FLAGS,
+:52-301 DataStruct, :417-667 ciphertext classes, :675-713 key classes).
+
+Only the layout contract is reproduced: `data` of a Ciphertext is [c0, c1], each a
+per-device list of int64 [limbs, N] tensors (a leading batch dimension is additionally accepted by
+the B200 engine); a KeySwitchKey's data is a list over global digit-group id of PublicKey objects
+whose data is [b_list, a_list] with [P, N] tensors.  Operator sugar, pickling and device moves of
+the reference classes are host conveniences outside the hot path.
+"""
+
+from __future__ import annotations
+
+from collections import defaultdict
+from enum import Flag, auto
+
+
+class FLAGS(Flag):
+    NTT_STATE = auto()
+    MONTGOMERY_STATE = auto()
+    INCLUDE_SPECIAL = auto()
+    NEED_RESCALE = auto()
+    NEED_RELINERIZE = auto()
+
+
+def _none():
+    return None
+
+
+class DataStruct:
+    def __init__(self, data=None, *, flags=None, level: int, **kwargs):
+        self.data = data
+        self._flags = FLAGS(0)
+        flags = flags or []
+        if isinstance(flags, list):
+            for f in flags:
+                self._flags |= f
+        elif isinstance(flags, FLAGS):
+            self._flags = flags
+        self.level = level
+        self.misc = defaultdict(_none)
+        if "misc" in kwargs:
+            self.misc.update(kwargs.pop("misc") or {})
+        self.misc.update(kwargs)
+
+    def has_flag(self, flag: FLAGS) -> bool:
+        return bool(self._flags & flag)
+
+    def set_flag(self, flag: FLAGS):
+        self._flags |= flag
+
+    def rm_flag(self, flag: FLAGS):
+        self._flags &= ~flag
+
+    def clone(self, clone_data: bool = True):
+        def cp(x):
+            if isinstance(x, list):
+                return [cp(y) for y in x]
+            return x.clone() if hasattr(x, "clone") else x
+
+        new = self.__class__(cp(self.data) if clone_data else [], flags=self._flags, level=self.level,
+                             misc=dict(self.misc))
+        return new
+
+    @classmethod
+    def wrap(cls, another: "DataStruct", **kwargs):
+        return cls(another.data, flags=another._flags, level=another.level, misc=dict(another.misc), **kwargs)
+
+
+class Ciphertext(DataStruct):
+    pass
+
+
+class CiphertextTriplet(DataStruct):
+    pass
+
+
+class Plaintext(DataStruct):
+    """Holds the per-level cache of the NTT+Montgomery encoding used by pc_mult
+    (tiberate/typing.py:318-409).  Encoding itself (float FFT) is outside the hot path: build one
+    with `Plaintext.from_ntt(level, tensor)`."""
+
+    def __init__(self, data=None, *, flags=None, level: int = 0, **kwargs):
+        super().__init__(data, flags=flags, level=level, **kwargs)
+        self.cache = defaultdict(dict)
+
+    @classmethod
+    def from_ntt(cls, level: int, pt_ntt):
+        pt = cls(None, level=level)
+        pt.cache[level]["pc_mult"] = pt_ntt if isinstance(pt_ntt, list) else [pt_ntt]
+        return pt
+
+
+class SecretKey(DataStruct):
+    pass
+
+
+class EvaluationKey(SecretKey):
+    pass
+
+
+class PublicKey(DataStruct):
+    pass
+
+
+class KeySwitchKey(DataStruct):
+    pass
+
+
+class RotationKey(KeySwitchKey):
+    @property
+    def delta(self):
+        return self.misc.get("delta")
+
+    @delta.setter
+    def delta(self, value):
+        self.misc["delta"] = value
+
+
+class ConjugationKey(DataStruct):
+    pass
