@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd_A(TbDev c, TbView src, TbView d
     for (int i = 0; i < 16; ++i) x[i] = tb_mm_ss(x[i], Rs, p.q4, p.k);
   }
   auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
-  tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.psi4 + ((long)g << c.logN), p, slot);
+  tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = x[i];
 }
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd_B(TbDev c, TbView src, TbView d
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
-  tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), p, slot);
+  tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_ntt_inv_B(TbDev c, TbView src, TbView d
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
-  tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, c.ipsi4 + ((long)g << c.logN), p, slot);
+  tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, c.ipsi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, f0))] = x[i];
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k_ntt_inv_A(TbDev c, TbView src, TbView d
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = s[(long)tb::tile_x(tr, i, 0) << c.LB];
   auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
-  tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, c.ipsi4 + ((long)g << c.logN), p, slot);
+  tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, c.ipsi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   const i64 Ninv = c.pr[g].Ninv;
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, f0) << c.LB] = intt_epilogue<EPI>(x[i], Ninv, p);

@@ -47,6 +47,15 @@ __device__ __forceinline__ void bfly_gs(i64& U, i64& V, u64 S4, const PrimeRegs&
   V = tb_mm_s4(o, S4, p.q4, p.k);
 }
 
+// Butterfly policy of the exposed, bit-exact transforms: the reference's lazy Montgomery butterflies.
+struct ExactPol {
+  PrimeRegs p;
+  typedef u64 TW;
+  static __device__ __forceinline__ TW load(const TW* t) { return __ldg(t); }
+  __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int /*mlog*/) const { bfly_ct(U, O, S, p); }
+  __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int /*mlog*/) const { bfly_gs(U, V, S, p); }
+};
+
 // field start of forward round r (r = 0 handles the largest distances)
 template <int LT>
 __host__ __device__ constexpr int fwd_field(int r) {
@@ -59,9 +68,9 @@ __host__ __device__ constexpr int num_rounds() {
 
 // One forward round: stages with local distance bits top .. top-ns+1 (descending).
 // mlog(d) = log2(number of groups) of the stage with local distance bit d.
-template <int LT, int R>
+template <int LT, int R, class POL>
 __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlog_of_d0,
-                                          const u64* __restrict__ tw, const PrimeRegs& p) {
+                                          const typename POL::TW* __restrict__ tw, const POL& p) {
   constexpr int f = fwd_field<LT>(R);
   constexpr int top = LT - 1 - 4 * R;
   constexpr int ns = (LT - 4 * R) > 4 ? 4 : (LT - 4 * R);
@@ -73,20 +82,20 @@ __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlo
     const int base = (1 << mlog) + (tile << (LT - 1 - d)) + ((t >> f) << (3 - b));
 #pragma unroll
     for (int g = 0; g < (8 >> b); ++g) {       // distinct twiddles: register bits above b
-      const u64 S4 = __ldg(tw + base + g);
+      const typename POL::TW S4 = POL::load(tw + base + g);
 #pragma unroll
       for (int l = 0; l < (1 << b); ++l) {     // register bits below b
         const int i = (g << (b + 1)) | l;
-        bfly_ct(x[i], x[i | (1 << b)], S4, p);
+        p.ct(x[i], x[i | (1 << b)], S4, mlog);
       }
     }
   }
 }
 
 // One inverse round: the same field as forward round R, stages ascending in distance.
-template <int LT, int R>
+template <int LT, int R, class POL>
 __device__ __forceinline__ void inv_round(i64 (&x)[16], int t, int tile, int mlog_of_d0,
-                                          const u64* __restrict__ tw, const PrimeRegs& p) {
+                                          const typename POL::TW* __restrict__ tw, const POL& p) {
   constexpr int f = fwd_field<LT>(R);
   constexpr int top = LT - 1 - 4 * R;
   constexpr int ns = (LT - 4 * R) > 4 ? 4 : (LT - 4 * R);
@@ -98,11 +107,11 @@ __device__ __forceinline__ void inv_round(i64 (&x)[16], int t, int tile, int mlo
     const int base = (1 << mlog) + (tile << (LT - 1 - d)) + ((t >> f) << (3 - b));
 #pragma unroll
     for (int g = 0; g < (8 >> b); ++g) {
-      const u64 S4 = __ldg(tw + base + g);
+      const typename POL::TW S4 = POL::load(tw + base + g);
 #pragma unroll
       for (int l = 0; l < (1 << b); ++l) {
         const int i = (g << (b + 1)) | l;
-        bfly_gs(x[i], x[i | (1 << b)], S4, p);
+        p.gs(x[i], x[i | (1 << b)], S4, mlog);
       }
     }
   }
@@ -122,9 +131,9 @@ __device__ __forceinline__ void exchange(i64 (&x)[16], i64* sm, int t, int fw, i
 
 // Full forward tile: rounds 0..NR-1.  On entry x is laid out with field fwd_field<LT>(0);
 // on exit with field fwd_field<LT>(NR-1) (== 0 unless LT == 4k where it is also 0).
-template <int LT, class SlotFn>
+template <int LT, class POL, class SlotFn>
 __device__ __forceinline__ void tile_fwd(i64 (&x)[16], i64* sm, int t, int tile, int mlog_of_d0,
-                                         const u64* __restrict__ tw, const PrimeRegs& p, SlotFn slot) {
+                                         const typename POL::TW* __restrict__ tw, const POL& p, SlotFn slot) {
   fwd_round<LT, 0>(x, t, tile, mlog_of_d0, tw, p);
   if constexpr (num_rounds<LT>() > 1) {
     exchange(x, sm, t, fwd_field<LT>(0), fwd_field<LT>(1), slot);
@@ -137,9 +146,9 @@ __device__ __forceinline__ void tile_fwd(i64 (&x)[16], i64* sm, int t, int tile,
 }
 
 // Full inverse tile: rounds NR-1..0.  Entry layout: field fwd_field<LT>(NR-1); exit: fwd_field<LT>(0).
-template <int LT, class SlotFn>
+template <int LT, class POL, class SlotFn>
 __device__ __forceinline__ void tile_inv(i64 (&x)[16], i64* sm, int t, int tile, int mlog_of_d0,
-                                         const u64* __restrict__ tw, const PrimeRegs& p, SlotFn slot) {
+                                         const typename POL::TW* __restrict__ tw, const POL& p, SlotFn slot) {
   if constexpr (num_rounds<LT>() > 2) {
     inv_round<LT, 2>(x, t, tile, mlog_of_d0, tw, p);
     exchange(x, sm, t, fwd_field<LT>(2), fwd_field<LT>(1), slot);
