@@ -67,6 +67,11 @@ int tb200_ctx_get_twiddles(const tb200_ctx*, int inverse, int prime, int64_t* ou
 int tb200_ctx_info(const tb200_ctx*, int32_t* out /*[8]: logN,N,P,K,LA,LB,device,num_groups*/);
 /* max ciphertexts processed per internal pass by the engine layer (workspace = chunk * ~730 limb rows) */
 int tb200_ctx_set_chunk(tb200_ctx*, int chunk);
+/* 1 (default): the fused engine calls run their internal transforms on the mod-q path (Harvey/Shoup
+ * butterflies, fused ModUp prologue, 128-bit key accumulation); 0: they are composed from the exact
+ * op-layer kernels.  Outputs are bit-identical either way (every internal chain ends in a
+ * canonicalising step); the switch exists for A/B tests and measurements. */
+int tb200_ctx_set_fast(tb200_ctx*, int on);
 
 /* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */
 enum tb200_pw_op {

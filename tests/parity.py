@@ -65,8 +65,8 @@ class Setup:
         self.rotk_d = {d: h.key(k, self.N) for d, k in self.rotk.items()}
 
     @classmethod
-    def toy(cls, h, logN, num_scales, K, seed=0, **kw):
-        return cls(h, logN, toy_primes(logN, num_scales, K), K, seed, **kw)
+    def toy(cls, h, logN, num_scales, K, seed=0, scale_bits=40, **kw):
+        return cls(h, logN, toy_primes(logN, num_scales, K, scale_bits=scale_bits), K, seed, **kw)
 
     def ct(self, level, batch=None):
         lp = self.octx.level_primes(level, False)

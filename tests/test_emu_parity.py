@@ -48,8 +48,21 @@ def test_pointwise_and_he_ops(h, logN, ns, K):
 def test_engine_every_level(h, logN, ns, K):
     s = Setup.toy(h, logN, ns, K, seed=200 + logN, rot_deltas=(1, 3))
     try:
-        for level in range(0, ns + 1):
-            parity.check_engine(s, level)
+        for fast in (True, False):  # internal mod-q path / exact op kernels: same bits
+            s.ctx.set_fast(fast)
+            for level in range(0, ns + 1):
+                parity.check_engine(s, level)
+    finally:
+        s.close()
+
+
+def test_engine_wide_scale_primes(h):
+    """55-bit "scale" primes: every limb takes the reducing (non-small) butterfly policy, with
+    multi-prime digit groups."""
+    s = Setup.toy(h, 8, 4, 3, seed=11, scale_bits=55)
+    try:
+        for level in (0, 2, 4):
+            parity.check_engine(s, level, ops=("keyswitch", "rotate", "cc_mult", "pc_mult"))
     finally:
         s.close()
 

@@ -146,6 +146,10 @@ class Tb200Context:
     def set_chunk(self, chunk: int):
         self.lib.check(self.lib.tb200_ctx_set_chunk(self.h, int(chunk)), "set_chunk")
 
+    def set_fast(self, on: bool):
+        """Internal transforms of the fused engine calls: mod-q path (default) or exact op kernels."""
+        self.lib.check(self.lib.tb200_ctx_set_fast(self.h, int(bool(on))), "set_fast")
+
     # ---- level helpers -------------------------------------------------------------------
     def rows_at(self, level: int, with_special: bool = False) -> int:
         return (self.P if with_special else self.num_ordinary) - level

@@ -124,6 +124,11 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   cudaFree(c->d_pir_sp);
   cudaFree(c->d_lenter);
   cudaFree(c->d_ks);
+  cudaFree(c->d_fp);
+  cudaFree(c->d_tw);
+  cudaFree(c->d_itw);
+  cudaFree(c->d_resc3);
+  cudaFree(c->d_lenter2);
   cudaFree(c->ws);
   delete c;
 }
@@ -184,6 +189,8 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
   c->psi.resize((size_t)P * N);
   c->ipsi.resize((size_t)P * N);
   std::vector<u64> psi4((size_t)P * N), ipsi4((size_t)P * N), series(N);
+  std::vector<TbTw2> tw2((size_t)P * N), itw2((size_t)P * N);
+  std::vector<TbFastPrime> fps(P);
   for (int g = 0; g < P; ++g) {
     const u64 qi = (u64)q[g];
     const u64 e = (qi - 1) / (2ull * N);
@@ -201,11 +208,28 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
       }
       std::vector<u64>& tab = dir == 0 ? c->psi : c->ipsi;
       std::vector<u64>& tab4 = dir == 0 ? psi4 : ipsi4;
+      std::vector<TbTw2>& t2 = dir == 0 ? tw2 : itw2;
       for (int i = 0; i < N; ++i) {
-        const i64 m = h_mm((i64)series[h_bitrev(i, logN)], c->primes[g].Rs, (i64)qi, c->k[g]);
+        const u64 plain = series[h_bitrev(i, logN)];
+        const i64 m = h_mm((i64)plain, c->primes[g].Rs, (i64)qi, c->k[g]);
         tab[(size_t)g * N + i] = (u64)m;
         tab4[(size_t)g * N + i] = (u64)m << 2;
+        t2[(size_t)g * N + i].w = plain;
+        t2[(size_t)g * N + i].ws = h_shoup(plain, qi);
       }
+    }
+    {
+      TbFastPrime& f = fps[g];
+      const u64 Rm = (u64)(Rbig % qi);
+      f.q = qi;
+      f.q2 = 2 * qi;
+      f.Rm = Rm;
+      f.Rm_s = h_shoup(Rm, qi);
+      f.ex = h_mulmod(h_invmod_prime((u64)N, qi), h_invmod_prime(Rm, qi), qi);
+      f.ex_s = h_shoup(f.ex, qi);
+      f.off = qi << (62 - h_bitlen(qi));
+      f.small = (qi >> 42) == 0 ? 1 : 0;
+      f.pad = 0;
     }
   }
   // rescale scales and P_k^-1 tables
@@ -214,6 +238,16 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
     for (int g = l + 1; g < no; ++g) {
       const u64 qg = (u64)q[g], Rm = (u64)(Rbig % qg);
       resc[(size_t)l * P + g] = (i64)h_mulmod(h_invmod_prime((u64)q[l] % qg, qg), Rm, qg);
+    }
+  std::vector<u64> resc3((size_t)no * P * 3, 0);
+  for (int l = 0; l < no; ++l)
+    for (int g = l + 1; g < no; ++g) {
+      const u64 qg = (u64)q[g], ql = (u64)q[l], Rm = (u64)(Rbig % qg);
+      const u64 c1 = h_mulmod(h_invmod_prime(ql % qg, qg), Rm, qg);
+      u64* r3 = &resc3[((size_t)l * P + g) * 3];
+      r3[0] = c1;
+      r3[1] = h_shoup(c1, qg);
+      r3[2] = qg * ((ql + qg - 1) / qg + 1);  // multiple of q_g above q_l (+ q_g of slack for tiny negatives)
     }
   for (int kk = 0; kk < K; ++kk)
     for (int g = 0; g < no + kk; ++g) {
@@ -224,6 +258,7 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
     for (int row = 0; row < kk; ++row) pirsp[(size_t)kk * K + row] = pir[(size_t)kk * P + no + row];
   // digit groups per level
   std::vector<i64> lenter;
+  std::vector<u64> lenter2;
   c->ks.resize(no);
   for (int l = 0; l < no; ++l) {
     TbKsLevel& lv = c->ks[l];
@@ -260,14 +295,21 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
         for (int g = 0; g < P; ++g) {
           const u64 qg = (u64)q[g];
           lenter.push_back((i64)h_mulmod(Lmod(i, qg), (u64)c->primes[g].Rs, qg));
+          const u64 C = h_mulmod(Lmod(i, qg), (u64)(Rbig % qg), qg);
+          lenter2.push_back(C);
+          lenter2.push_back(h_shoup(C, qg));
         }
     }
   }
   if (lenter.empty()) lenter.push_back(0);
+  if (lenter2.empty()) lenter2.push_back(0);
   bool ok = upload(&c->d_primes, c->primes) == cudaSuccess && upload(&c->d_psi4, psi4) == cudaSuccess &&
             upload(&c->d_ipsi4, ipsi4) == cudaSuccess && upload(&c->d_rescale, resc) == cudaSuccess &&
             upload(&c->d_pir, pir) == cudaSuccess && upload(&c->d_pir_sp, pirsp) == cudaSuccess &&
-            upload(&c->d_lenter, lenter) == cudaSuccess && upload(&c->d_ks, c->ks) == cudaSuccess;
+            upload(&c->d_lenter, lenter) == cudaSuccess && upload(&c->d_ks, c->ks) == cudaSuccess &&
+            upload(&c->d_fp, fps) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
+            upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
+            upload(&c->d_lenter2, lenter2) == cudaSuccess;
   if (!ok) {
     fail(TB200_ENOMEM, "ctx_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     tb200_ctx_destroy(c);
@@ -302,6 +344,12 @@ extern "C" int tb200_ctx_info(const tb200_ctx* c, int32_t* out) {
 extern "C" int tb200_ctx_set_chunk(tb200_ctx* c, int chunk) {
   if (!c || chunk < 1) return fail(TB200_EINVAL, "chunk must be >= 1");
   c->chunk = chunk;
+  return 0;
+}
+
+extern "C" int tb200_ctx_set_fast(tb200_ctx* c, int on) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  c->fast = on != 0;
   return 0;
 }
 
@@ -541,6 +589,91 @@ extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const t
   return 0;
 }
 
+// ---- fast (mod-q) transforms ------------------------------------------------------------------------
+template <int PRO>
+static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gridz, tb200_stream st) {
+  const int lw = ntt_lw(c);
+  a.LW = lw;
+  const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)gridz), block(1u << (c->LA - 4 + lw));
+  switch (c->LA) {
+#define ACASE(n)                                                        \
+  case n: {                                                             \
+    auto kfn = k_fast_fwd_A<n, PRO>;                                    \
+    LAUNCHN("k_fast_fwd_A", kfn, grid, block, st, c->devf(), a);        \
+  } break;
+    ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
+#undef ACASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LA %d", c->LA);
+  }
+  return 0;
+}
+static int launch_fast_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
+                             tb200_stream st) {
+  const int lw = ntt_lw(c);
+  const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
+  switch (c->LA) {
+#define ACASE(n)                                                                        \
+  case n: {                                                                             \
+    auto kfn = k_fast_inv_A<n>;                                                         \
+    LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw);     \
+  } break;
+    ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
+#undef ACASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LA %d", c->LA);
+  }
+  return 0;
+}
+static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
+                         tb200_stream st) {
+  const int te = c->N < TB_TILE ? c->N : TB_TILE;
+  const dim3 grid((unsigned)(c->N / te), (unsigned)rows, (unsigned)batch), block((unsigned)(te / 16));
+  switch (c->LB) {
+#define BCASE(n)                                                                  \
+  case n: {                                                                       \
+    if (inverse) {                                                                \
+      auto kfn = k_fast_inv_B<n>;                                                 \
+      LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0); \
+    } else {                                                                      \
+      auto kfn = k_fast_fwd_B<n>;                                                 \
+      LAUNCHN("k_fast_fwd_B", kfn, grid, block, st, c->devf(), src, dst, prime0); \
+    }                                                                             \
+  } break;
+    BCASE(4) BCASE(5) BCASE(6) BCASE(7) BCASE(8)
+#undef BCASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LB %d", c->LB);
+  }
+  return 0;
+}
+// forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
+static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
+                              int rescale_level, tb200_stream st) {
+  TbFwdAArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = src;
+  a.dst = dst;
+  a.prime0 = prime0;
+  a.ngroups = 1;
+  int rc;
+  if (rescale_level >= 0) {
+    a.resc = c->d_resc3 + ((size_t)rescale_level * c->P + rescale_level + 1) * 3;
+    a.round_at = (i64)(c->q[rescale_level] / 2);
+    rc = launch_fast_fwd_A<TB_FPRO_RESCALE_ENTER>(c, a, rows, batch, st);
+  } else {
+    rc = launch_fast_fwd_A<TB_FPRO_ENTER>(c, a, rows, batch, st);
+  }
+  if (rc) return rc;
+  return launch_fast_B(c, false, dst, dst, rows, batch, prime0, st);
+}
+static int fast_inverse_exit(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
+                             tb200_stream st) {
+  int rc = launch_fast_B(c, true, src, dst, rows, batch, prime0, st);
+  if (rc) return rc;
+  return launch_fast_inv_A(c, dst, dst, rows, batch, prime0, st);
+}
+
 // ---- fused HE ops ---------------------------------------------------------------------------------
 extern "C" int tb200_rescale_rows(tb200_ctx* c, int rows, int prime0, const tb200_poly* a, const int64_t* scales,
                                   const int64_t* rescaler, int64_t round_at, int exact, tb200_stream st) {
@@ -692,6 +825,25 @@ static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKs
   // 1. digits
   LAUNCH(k_digits, dim3((unsigned)((N + 255) / 256), (unsigned)ng, (unsigned)nb), dim3(256), st, d, dlv, a,
          dense(state, L, N), level, N);
+  if (c->fast) {
+    // 2+3. ModUp extend fused into forward pass A, then pass B (mod-q path)
+    TbFwdAArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.src = dense(state, L, N);
+    fa.dst = dense(ext, E, N);
+    fa.lv = dlv;
+    fa.lenter2 = c->d_lenter2;
+    fa.prime0 = level;
+    fa.ngroups = ng;
+    int rcf = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st);
+    if (rcf) return rcf;
+    if ((rcf = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, level, st))) return rcf;
+    // 4. key inner product, 128-bit accumulation over the groups
+    LAUNCH(k_fast_mac, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)nb),
+           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, level, N, E);
+    // 5. back to coefficients, canonical
+    if ((rcf = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, st))) return rcf;
+  } else {
   // 2. extend every group to the L+K limbs
   LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
          dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, dense(state, L, N), ext, level, N, E);
@@ -704,6 +856,8 @@ static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKs
   // 5. back to coefficients, canonical
   rc = ntt_inverse(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, 2, st);
   if (rc) return rc;
+  }
+  int rc = 0;
   // 6. ModDown (+ fused tail)
   for (int h = 0; h < 2; ++h) {
     TbView cc;
@@ -811,7 +965,7 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
 
 // forward transforms + tensor product of one chunk; x: 4 polys [4][nb][L][N] workspace (x0,x1,y0,y1)
 static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbView b0, TbView b1, int pre_rescale,
-                      i64* x, TbView d0, TbView d1, TbView d2, tb200_stream st) {
+                      i64* x, TbView d0, TbView d1, TbView d2, bool fast, tb200_stream st) {
   const int N = c->N;
   const int lvl = level + (pre_rescale ? 1 : 0);
   const int L = c->num_ord - lvl;
@@ -819,7 +973,10 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
   TbView in[4] = {a0, a1, b0, b1};
   for (int i = 0; i < 4; ++i) {
     TbView xi = dense(x + i * pe, L, N);
-    if (pre_rescale) {
+    if (fast) {
+      int rc = fast_forward_enter(c, in[i], xi, L, nb, lvl, pre_rescale ? level : -1, st);
+      if (rc) return rc;
+    } else if (pre_rescale) {
       rescale_impl(c, level, nb, in[i], xi, 1, st);
       int rc = ntt_forward(c, xi, xi, L, nb, lvl, true, st);
       if (rc) return rc;
@@ -853,7 +1010,7 @@ extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const t
   for (int b = 0; b < batch; b += ch) {
     const int nb = batch - b < ch ? batch - b : ch;
     rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
-                    pre_rescale, c->ws, shift(view(d0), b), shift(view(d1), b), shift(view(d2), b), st);
+                    pre_rescale, c->ws, shift(view(d0), b), shift(view(d1), b), shift(view(d2), b), false, st);
     if (rc) return rc;
   }
   POST();
@@ -865,7 +1022,8 @@ static int relin_chunk(tb200_ctx* c, int lvl, int nb, i64* d, const TbKskDev& ke
                        tb200_stream st) {
   const int N = c->N, L = c->num_ord - lvl;
   const size_t pe = (size_t)nb * L * N;
-  int rc = ntt_inverse(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, 2, st);
+  int rc = c->fast ? fast_inverse_exit(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, st)
+                   : ntt_inverse(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, 2, st);
   if (rc) return rc;
   return keyswitch_chunk(c, lvl, nb, dense(d + 2 * pe, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1, 1,
                          ksws, st);
@@ -936,7 +1094,7 @@ extern "C" int tb200_cc_mult_relin(tb200_ctx* c, int level, int batch, const tb2
     i64* d = x + 4 * pe;
     i64* ksws = d + 3 * pe;
     rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
-                    pre_rescale, x, dense(d, L, N), dense(d + pe, L, N), dense(d + 2 * pe, L, N), st);
+                    pre_rescale, x, dense(d, L, N), dense(d + pe, L, N), dense(d + 2 * pe, L, N), c->fast != 0, st);
     if (rc) return rc;
     rc = relin_chunk(c, lvl, nb, d, key, shift(view(out0), b), shift(view(out1), b), ksws, st);
     if (rc) return rc;
@@ -967,7 +1125,9 @@ extern "C" int tb200_pc_mult(tb200_ctx* c, int level, int batch, const tb200_pol
     const tb200_poly* out[2] = {out0, out1};
     for (int h = 0; h < 2; ++h) {
       TbView x = dense(c->ws + h * pe, L, N);
-      if ((rc = ntt_forward(c, shift(view(in[h]), b), x, L, nb, level, true, st))) return rc;
+      rc = c->fast ? fast_forward_enter(c, shift(view(in[h]), b), x, L, nb, level, -1, st)
+                   : ntt_forward(c, shift(view(in[h]), b), x, L, nb, level, true, st);
+      if (rc) return rc;
       TbPwArgs g;
       memset(&g, 0, sizeof(g));
       TbView ptv = view(pt);
@@ -979,7 +1139,8 @@ extern "C" int tb200_pc_mult(tb200_ctx* c, int level, int batch, const tb200_pol
       g.N = N;
       launch_pw<0>(c, g, L, nb, st);
       TbView dst = post_rescale ? x : shift(view(out[h]), b);
-      if ((rc = ntt_inverse(c, x, dst, L, nb, level, 2, st))) return rc;
+      rc = c->fast ? fast_inverse_exit(c, x, dst, L, nb, level, st) : ntt_inverse(c, x, dst, L, nb, level, 2, st);
+      if (rc) return rc;
       if (post_rescale) rescale_impl(c, level, nb, x, shift(view(out[h]), b), 1, st);
     }
   }

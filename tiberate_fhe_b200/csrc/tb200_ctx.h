@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "tb200_kernels.cuh"
+#include "tb200_kernels_fast.cuh"
 
 typedef __int128 i128;
 typedef unsigned __int128 u128;
@@ -43,6 +43,15 @@ static inline i64 h_mm(i64 a, i64 b, i64 q, u64 k) {
   const i128 t = x + (i128)((u128)s * (u128)(u64)q);
   return (i64)(t >> 62);
 }
+static inline u64 h_shoup(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+static inline int h_bitlen(u64 x) {
+  int n = 0;
+  while (x) {
+    ++n;
+    x >>= 1;
+  }
+  return n;
+}
 static inline int h_bitrev(int x, int bits) {
   int r = 0;
   for (int i = 0; i < bits; ++i) {
@@ -69,8 +78,25 @@ struct tb200_ctx {
   i64* d_pir_sp = nullptr;   // [K][K]  (k, row)
   i64* d_lenter = nullptr;   // all groups' L_enter blocks
   TbKsLevel* d_ks = nullptr; // [num_ord]
+  // fast (mod-q) path tables
+  int fast = 1;
+  TbFastPrime* d_fp = nullptr;
+  TbTw2 *d_tw = nullptr, *d_itw = nullptr;
+  u64* d_resc3 = nullptr;    // [num_ord][P][3]: (q_l^-1 R mod q_g, Shoup companion, offset) per (level l, prime g)
+  u64* d_lenter2 = nullptr;  // (L_{k-1} R mod q_g, Shoup companion) pairs, same indexing as d_lenter
   i64* ws = nullptr;         // engine workspace
   size_t ws_elems = 0;
+  TbDevFast devf() const {
+    TbDevFast d;
+    d.fp = d_fp;
+    d.tw = d_tw;
+    d.itw = d_itw;
+    d.logN = logN;
+    d.LA = LA;
+    d.LB = LB;
+    d.P = P;
+    return d;
+  }
   TbDev dev() const {
     TbDev d;
     d.pr = d_primes;

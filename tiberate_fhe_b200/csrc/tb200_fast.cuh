@@ -1,0 +1,95 @@
+// tb200_fast.cuh -- the internal ("mod-q") transform path of the fused engine calls.
+//
+// Inside cc_mult+relinearize, switch_key and rotate_single every NTT-domain intermediate is consumed
+// by a step that canonicalises: the reference ends each chain with intt_radix2_exit_reduce
+// (mont_used_in_ntt.cuh:172-206) or the ModDown (he_fused_cuda.cu:471-519), whose outputs depend only
+// on the residue class of their inputs.  So between the (exact, integer) ModUp digits and those
+// canonicalising steps only values modulo q matter, and the butterflies need not reproduce the
+// reference's lazy Montgomery representatives.  This path uses Harvey butterflies with Shoup
+// twiddles (w, w' = floor(w 2^64 / q)):  V = O*w - umulhi(O, w')*q  in [0, 2q) for ANY 64-bit O,
+//   * "small" primes (q < 2^42, the 40-bit scale primes = 34 of 39 limbs at logN16): no conditional
+//     subtraction at all -- forward values grow by 2q per stage (< 36q < 2^47 after 17 stages),
+//     inverse values double per stage (< 2^(2+17) q < 2^61);
+//   * other primes (the 60-bit base / special primes): one conditional subtraction per butterfly,
+//     values in [0, 4q) (forward) / [0, 2q) (inverse).
+// 10 IMAD + ~12 ALU instructions per butterfly instead of 20 + 35 for the exact one.
+// The exposed ops (tb200_ntt / tb200_intt / cc_mult_triplet) keep the exact butterflies.
+#pragma once
+#include "tb200_ntt.cuh"
+
+struct __align__(16) TbTw2 {
+  u64 w;   // plain twiddle psi^brev(k) mod q (canonical)
+  u64 ws;  // floor(w * 2^64 / q)
+};
+
+// per-prime constants of the fast path
+struct __align__(16) TbFastPrime {
+  u64 q, q2;
+  u64 Rm, Rm_s;      // R mod q and its Shoup companion              (enter: x -> x R)
+  u64 ex, ex_s;      // N^-1 R^-1 mod q                             (exit of the inverse transform)
+  u64 off;           // q << (62 - bitlen(q)): multiple of q in [2^61, 2^62) making signed digits non-negative
+  int small;         // q < 2^42
+  int pad;
+};
+
+namespace tb {
+
+__device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws, u64 q) {
+  const u64 h = __umul64hi(x, ws);
+  return x * w - h * q;  // in [0, 2q)
+}
+
+__device__ __forceinline__ TbTw2 load_tw2(const TbTw2* p) {
+#ifndef TB200_HOST_EMU
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  TbTw2 r;
+  r.w = v.x;
+  r.ws = v.y;
+  return r;
+#else
+  return *p;
+#endif
+}
+
+// q < 2^42: no reductions.  Forward: values < B0 + 2q * stages.  Inverse: inputs < 4q, the bound
+// doubles per stage; `off` = q << (2 + stage) keeps U - V non-negative and is a multiple of q.
+struct FastSmallPol {
+  u64 q, q2;
+  int logN;
+  typedef TbTw2 TW;
+  static __device__ __forceinline__ TW load(const TW* t) { return load_tw2(t); }
+  __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
+    const u64 u = (u64)U, v = shoup((u64)O, S.w, S.ws, q);
+    U = (i64)(u + v);
+    O = (i64)(u + q2 - v);
+  }
+  __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int mlog) const {
+    const u64 u = (u64)U, v = (u64)V;
+    const u64 off = q << (2 + (logN - 1 - mlog));
+    U = (i64)(u + v);
+    V = (i64)shoup(u + off - v, S.w, S.ws, q);
+  }
+};
+
+// any q < 2^60: Harvey lazy butterflies, forward values in [0, 4q), inverse values in [0, 2q).
+struct FastBigPol {
+  u64 q, q2;
+  typedef TbTw2 TW;
+  static __device__ __forceinline__ TW load(const TW* t) { return load_tw2(t); }
+  __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
+    u64 u = (u64)U;
+    u = (u >= q2) ? u - q2 : u;
+    const u64 v = shoup((u64)O, S.w, S.ws, q);
+    U = (i64)(u + v);
+    O = (i64)(u + q2 - v);
+  }
+  __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int) const {
+    const u64 u = (u64)U, v = (u64)V;
+    u64 a = u + v;
+    a = (a >= q2) ? a - q2 : a;
+    U = (i64)a;
+    V = (i64)shoup(u + q2 - v, S.w, S.ws, q);
+  }
+};
+
+}  // namespace tb

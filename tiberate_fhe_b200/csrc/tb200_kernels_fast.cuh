@@ -1,0 +1,245 @@
+// tb200_kernels_fast.cuh -- kernels of the internal mod-q path (see tb200_fast.cuh for why it is
+// allowed and what it saves).  Same tiling as the exact transforms in tb200_kernels.cuh.
+#pragma once
+#include "tb200_fast.cuh"
+#include "tb200_kernels.cuh"
+
+struct TbDevFast {
+  const TbFastPrime* fp;  // [P]
+  const TbTw2* tw;        // [P][N] forward twiddles (plain + Shoup)
+  const TbTw2* itw;       // [P][N] inverse twiddles
+  int logN, LA, LB, P;
+};
+
+#define TB_FPRO_ENTER 0          // x = (a + q) * R                         (enter_ntt_radix2, mod q)
+#define TB_FPRO_RESCALE_ENTER 1  // x = ((a - r) q_l^-1 + [r > q_l/2]) * R  (rescale + enter, mod q)
+#define TB_FPRO_EXTEND 2         // x = sum_k d_k * (L_{k-1} R)             (ModUp extend, mod q)
+
+struct TbFwdAArgs {
+  TbView src, dst;
+  const u64* resc;        // RESCALE_ENTER: per limb row (c1, c1', off) triples for this level
+  i64 round_at;           // RESCALE_ENTER: q_l / 2
+  const TbKsLevel* lv;    // EXTEND
+  const u64* lenter2;     // EXTEND: (C, C') pairs, indexed (G.lenter_off + (k-1) P + prime)
+  int prime0, LW, ngroups;
+};
+
+template <int PRO>
+__device__ __forceinline__ i64 fast_prologue(const TbFwdAArgs& a, const TbFastPrime& P, int bt, int gi, int limb,
+                                             long col_off, int g, int nP) {
+  if constexpr (PRO == TB_FPRO_ENTER) {
+    const i64 v = a.src.row(bt, limb)[col_off];
+    return (i64)tb::shoup((u64)(v + (i64)P.q), P.Rm, P.Rm_s, P.q);
+  } else if constexpr (PRO == TB_FPRO_RESCALE_ENTER) {
+    const i64 v = a.src.row(bt, limb + 1)[col_off];
+    const i64 r = a.src.row(bt, 0)[col_off];
+    const u64* c = a.resc + 3 * limb;
+    u64 x = tb::shoup((u64)(v - r + (i64)c[2]), c[0], c[1], P.q);
+    x += (r > a.round_at) ? P.Rm : 0ull;
+    return (i64)x;
+  } else {
+    const TbKsGroup& G = a.lv->g[gi];
+    const i64 d0 = a.src.row(bt, G.first_row)[col_off];
+    u64 x = tb::shoup((u64)(d0 + (i64)P.off), P.Rm, P.Rm_s, P.q);
+    const u64* le = a.lenter2 + 2 * (G.lenter_off + g);
+    for (int k = 1; k < G.alpha; ++k) {
+      const i64 d = a.src.row(bt, G.first_row + k)[col_off];
+      x += tb::shoup((u64)(d + (i64)P.off), le[0], le[1], P.q);
+      if (!P.small) x = (x >= P.q2) ? x - P.q2 : x;
+      le += 2 * nP;
+    }
+    return (i64)x;
+  }
+}
+
+// forward pass A with a fused prologue.  EXTEND: grid.z = batch * ngroups, dst batch index = grid.z.
+template <int LA, int PRO>
+__global__ void __launch_bounds__(256) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int W = 1 << a.LW;
+  const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> a.LW;
+  const int limb = blockIdx.y, g = a.prime0 + limb;
+  const TbFastPrime P = c.fp[g];
+  int bt = blockIdx.z, gi = 0;
+  if constexpr (PRO == TB_FPRO_EXTEND) {
+    gi = blockIdx.z % a.ngroups;
+    bt = blockIdx.z / a.ngroups;
+  }
+  const long c0 = (long)blockIdx.x * W + col;
+  i64* d = a.dst.row(blockIdx.z, limb) + c0;
+  constexpr int f0 = tb::fwd_field<LA>(0);
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((long)tb::tile_x(tr, i, f0) << c.LB) + c0, g, c.P);
+  auto slot = [&](int lx) { return tb::pad16((lx << a.LW) | col); };
+  const TbTw2* tw = c.tw + ((long)g << c.logN);
+  if (P.small)
+    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+  else
+    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = x[i];
+}
+
+// forward pass B; outputs: small primes < 38q, other primes reduced to [0, 2q).
+template <int LB>
+__global__ void __launch_bounds__(256) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst, int prime0) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime P = c.fp[g];
+  const long e0 = (long)blockIdx.x * nt * 16;
+  const i64* s = src.row(blockIdx.z, limb) + e0;
+  i64* d = dst.row(blockIdx.z, limb) + e0;
+  const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
+  const int tile = (int)(e0 >> LB) + blk;
+  auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
+  constexpr int f0 = tb::fwd_field<LB>(0);
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm[tb::pad16(i * nt + tid)] = s[i * nt + tid];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
+  const TbTw2* tw = c.tw + ((long)g << c.logN);
+  if (P.small) {
+    tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+  } else {
+    tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[i * nt + tid] = sm[tb::pad16(i * nt + tid)];
+}
+
+// inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
+template <int LB>
+__global__ void __launch_bounds__(256) k_fast_inv_B(TbDevFast c, TbView src, TbView dst, int prime0) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime P = c.fp[g];
+  const long e0 = (long)blockIdx.x * nt * 16;
+  const i64* s = src.row(blockIdx.z, limb) + e0;
+  i64* d = dst.row(blockIdx.z, limb) + e0;
+  const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
+  const int tile = (int)(e0 >> LB) + blk;
+  auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
+  constexpr int f0 = tb::fwd_field<LB>(0);
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const i64 v = s[i * nt + tid];
+    sm[tb::pad16(i * nt + tid)] = v < 0 ? v + (i64)P.q2 : v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
+  const TbTw2* tw = c.itw + ((long)g << c.logN);
+  if (P.small)
+    tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+  else
+    tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, f0))] = x[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[i * nt + tid] = sm[tb::pad16(i * nt + tid)];
+}
+
+// inverse pass A' + exit: y = CS1(x * N^-1 R^-1)  == intt_radix2_exit_reduce of the reference (canonical).
+template <int LA>
+__global__ void __launch_bounds__(256) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LW) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int W = 1 << LW;
+  const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime P = c.fp[g];
+  const i64* s = src.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  i64* d = dst.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  constexpr int f0 = tb::fwd_field<LA>(0);
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = s[(long)tb::tile_x(tr, i, 0) << c.LB];
+  auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
+  const TbTw2* tw = c.itw + ((long)g << c.logN);
+  if (P.small)
+    tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+  else
+    tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const u64 y = tb::shoup((u64)x[i], P.ex, P.ex_s, P.q);
+    d[(long)tb::tile_x(tr, i, f0) << c.LB] = (i64)(y >= P.q ? y - P.q : y);
+  }
+}
+
+// Montgomery reduction of a signed 128-bit T (|T| < 2^124): (T + ((T k) mod 2^62) q) / 2^62
+__device__ __forceinline__ i64 tb_montred128(__int128 T, u64 q4, u64 k) {
+  const u64 lo = (u64)T;
+  const i64 hi = (i64)(T >> 64);
+  const u64 s = (lo * k) & TB_MASK62;
+  const u64 t = __umul64hi(s, q4);
+  return (i64)(((u64)hi << 2) | (lo >> 62)) + (i64)t + ((lo & TB_MASK62) != 0 ? 1 : 0);
+}
+
+// x in (-2q, 4q) -> [0, 2q)   (key residues may be negative: mont_sub keeps negatives)
+__device__ __forceinline__ i64 tb_norm2q(i64 x, i64 q2) {
+  x = (x >= q2) ? x - q2 : x;
+  return (x < 0) ? x + q2 : x;
+}
+
+// key inner product, mod q: small primes accumulate the 128-bit products over the digit groups and
+// reduce once; other primes reduce per term.  Output lazy residues in [0, 2q + small).
+__global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
+                                                  const i64* ext, i64* acc, int level, int N, int rowsE) {
+  const int t = blockIdx.y, bt = blockIdx.z;
+  const TbPrime& P = c.pr[level + t];
+  const int small = f.fp[level + t].small;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (j >= N) return;
+  const int ng = lv->ngroups;
+  longlong2 o0, o1;
+  if (small) {
+    __int128 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    for (int gi = 0; gi < ng; ++gi) {
+      const int gid = lv->g[gi].gid;
+      const longlong2 e = *reinterpret_cast<const longlong2*>(ext + (((long)bt * ng + gi) * rowsE + t) * N + j);
+      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + (long)(level + t) * key.rs + j);
+      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + (long)(level + t) * key.rs + j);
+      a0x += (__int128)e.x * kb.x;
+      a0y += (__int128)e.y * kb.y;
+      a1x += (__int128)e.x * ka.x;
+      a1y += (__int128)e.y * ka.y;
+    }
+    o0.x = tb_montred128(a0x, P.q4, P.k) + P.q;
+    o0.y = tb_montred128(a0y, P.q4, P.k) + P.q;
+    o1.x = tb_montred128(a1x, P.q4, P.k) + P.q;
+    o1.y = tb_montred128(a1y, P.q4, P.k) + P.q;
+  } else {
+    i64 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    for (int gi = 0; gi < ng; ++gi) {
+      const int gid = lv->g[gi].gid;
+      const longlong2 e = *reinterpret_cast<const longlong2*>(ext + (((long)bt * ng + gi) * rowsE + t) * N + j);
+      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + (long)(level + t) * key.rs + j);
+      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + (long)(level + t) * key.rs + j);
+      a0x = tb_norm2q(a0x + tb_mm_ss(e.x, kb.x, P.q4, P.k), P.q2);
+      a0y = tb_norm2q(a0y + tb_mm_ss(e.y, kb.y, P.q4, P.k), P.q2);
+      a1x = tb_norm2q(a1x + tb_mm_ss(e.x, ka.x, P.q4, P.k), P.q2);
+      a1y = tb_norm2q(a1y + tb_mm_ss(e.y, ka.y, P.q4, P.k), P.q2);
+    }
+    o0.x = a0x;
+    o0.y = a0y;
+    o1.x = a1x;
+    o1.y = a1y;
+  }
+  *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 0) * rowsE + t) * N + j) = o0;
+  *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 1) * rowsE + t) * N + j) = o1;
+}
