@@ -254,13 +254,15 @@ def run_ours(args):
         kern[name] = (int(cnt), float(tot))
     tot_ms = sum(v[1] for v in kern.values()) or 1.0
     shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])}
+    kernel_us_per_op = {k: round(1e3 * v[1] / (B * psteps), 2) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])}
     top = max(kern, key=lambda k_: kern[k_][1]) if kern else None
     peak, peak_src = measured_peaks()
     # limbs transformed per HMult by each NTT pass kernel (DESIGN.md "Kernels"): forward passes see
     # 4 L (inputs) + ngroups (L+K) (ModUp) limbs, inverse passes 3 L + 2 (L+K); 16 B per residue.
     E = L + K
     limbs = {"k_ntt_fwd_A": 4 * L + ng * E, "k_ntt_fwd_B": 4 * L + ng * E, "k_ntt_inv_A": 3 * L + 2 * E,
-             "k_ntt_inv_B": 3 * L + 2 * E}
+             "k_ntt_inv_B": 3 * L + 2 * E, "k_fast_fwd_A": 4 * L + ng * E, "k_fast_fwd_B": 4 * L + ng * E,
+             "k_fast_inv_A": 3 * L + 2 * E, "k_fast_inv_B": 3 * L + 2 * E}
     roof = None
     if top in limbs:
         nl, tms = kern[top]
@@ -317,7 +319,7 @@ def run_ours(args):
                        "sharding": "ciphertext batch, no data-path collective",
                        "l2": "inputs (>= 17 GiB per step at batch 256) exceed the 126 MB L2"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "cpu_baseline": cpu, "kernel_time_share": shares,
+            "cpu_baseline": cpu, "kernel_time_share": shares, "kernel_us_per_op": kernel_us_per_op,
             "hmult_hbm_roofline": {"algorithmic_bytes_per_op": alg_bytes, "roofline_ops_per_s": peak * 1e9 / alg_bytes,
                                    "frac": value / world / (peak * 1e9 / alg_bytes)},
             "extra": extra,

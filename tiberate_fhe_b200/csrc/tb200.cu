@@ -129,6 +129,7 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   cudaFree(c->d_itw);
   cudaFree(c->d_resc3);
   cudaFree(c->d_lenter2);
+  cudaFree(c->d_bn);
   cudaFree(c->ws);
   delete c;
 }
@@ -256,6 +257,20 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
     }
   for (int kk = 0; kk < K; ++kk)
     for (int row = 0; row < kk; ++row) pirsp[(size_t)kk * K + row] = pir[(size_t)kk * P + no + row];
+  // ModDown in product form: B_k = prod_{j<=k} P_j^-1 mod q_g
+  std::vector<u64> bn((size_t)(K + 1) * P * 2, 0);
+  for (int g = 0; g < no; ++g) {
+    const u64 qg = (u64)q[g];
+    u64 B = 1;
+    for (int kk = 0; kk < K; ++kk) {
+      B = h_mulmod(B, h_invmod_prime((u64)q[no + kk] % qg, qg), qg);
+      const u64 neg = (qg - B) % qg;
+      bn[((size_t)kk * P + g) * 2] = neg;
+      bn[((size_t)kk * P + g) * 2 + 1] = h_shoup(neg, qg);
+    }
+    bn[((size_t)K * P + g) * 2] = B;
+    bn[((size_t)K * P + g) * 2 + 1] = h_shoup(B, qg);
+  }
   // digit groups per level
   std::vector<i64> lenter;
   std::vector<u64> lenter2;
@@ -309,7 +324,7 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
             upload(&c->d_lenter, lenter) == cudaSuccess && upload(&c->d_ks, c->ks) == cudaSuccess &&
             upload(&c->d_fp, fps) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
             upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
-            upload(&c->d_lenter2, lenter2) == cudaSuccess;
+            upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
   if (!ok) {
     fail(TB200_ENOMEM, "ctx_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     tb200_ctx_destroy(c);
@@ -722,6 +737,18 @@ static int moddown(tb200_ctx* c, int level, int batch, TbView cc, TbView p, TbVi
   const int L = c->num_ord - level;
   LAUNCH(k_chain_backward, grid_pw(c, 1, batch, 1), dim3(256), st, c->dev(), p, (const i64*)c->d_pir_sp, c->K,
          c->num_ord, c->N);
+  if (c->fast) {
+    const dim3 g2 = grid_pw(c, L, batch, 2);
+    const dim3 b2(c->N / 2 < 256 ? c->N / 2 : 256);
+    if (tail == 0) {
+      LAUNCH(k_fast_divide_by_p<0>, g2, b2, st, c->devf(), cc, p, add, out, (const u64*)c->d_bn, c->K, level, c->N);
+    } else if (tail == 1) {
+      LAUNCH(k_fast_divide_by_p<1>, g2, b2, st, c->devf(), cc, p, add, out, (const u64*)c->d_bn, c->K, level, c->N);
+    } else {
+      LAUNCH(k_fast_divide_by_p<2>, g2, b2, st, c->devf(), cc, p, add, out, (const u64*)c->d_bn, c->K, level, c->N);
+    }
+    return 0;
+  }
   const dim3 grid = grid_pw(c, L, batch, 1);
   if (tail == 0) {
     LAUNCH(k_divide_by_p<0>, grid, dim3(256), st, c->dev(), cc, p, add, out, (const i64*)c->d_pir, c->K, level, c->N);
@@ -839,8 +866,8 @@ static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKs
     if (rcf) return rcf;
     if ((rcf = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, level, st))) return rcf;
     // 4. key inner product, 128-bit accumulation over the groups
-    LAUNCH(k_fast_mac, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)nb),
-           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, level, N, E);
+    LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),
+           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, level, N, E, nb);
     // 5. back to coefficients, canonical
     if ((rcf = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, st))) return rcf;
   } else {

@@ -83,6 +83,7 @@ struct tb200_ctx {
   TbFastPrime* d_fp = nullptr;
   TbTw2 *d_tw = nullptr, *d_itw = nullptr;
   u64* d_resc3 = nullptr;    // [num_ord][P][3]: (q_l^-1 R mod q_g, Shoup companion, offset) per (level l, prime g)
+  u64* d_bn = nullptr;       // ModDown: [(K+1)][P][2] (-B_k mod q, Shoup) k < K, then (B_{K-1}, Shoup)
   u64* d_lenter2 = nullptr;  // (L_{k-1} R mod q_g, Shoup companion) pairs, same indexing as d_lenter
   i64* ws = nullptr;         // engine workspace
   size_t ws_elems = 0;

@@ -38,23 +38,49 @@ __device__ __forceinline__ i64 fast_prologue(const TbFwdAArgs& a, const TbFastPr
     x += (r > a.round_at) ? P.Rm : 0ull;
     return (i64)x;
   } else {
-    const TbKsGroup& G = a.lv->g[gi];
-    const i64 d0 = a.src.row(bt, G.first_row)[col_off];
-    u64 x = tb::shoup((u64)(d0 + (i64)P.off), P.Rm, P.Rm_s, P.q);
-    const u64* le = a.lenter2 + 2 * (G.lenter_off + g);
-    for (int k = 1; k < G.alpha; ++k) {
-      const i64 d = a.src.row(bt, G.first_row + k)[col_off];
-      x += tb::shoup((u64)(d + (i64)P.off), le[0], le[1], P.q);
-      if (!P.small) x = (x >= P.q2) ? x - P.q2 : x;
-      le += 2 * nP;
+    return 0;  // EXTEND is handled by extend_prologue<ALPHA> (all 16 residues of a thread at once)
+  }
+}
+
+// ModUp extend for the 16 residues of a thread, ALPHA digits each: loads first, then the Shoup sums.
+template <int ALPHA>
+__device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& a, const TbFastPrime& P,
+                                                const TbKsGroup& G, int bt, int g, int nP, int tr, int f0, int LB,
+                                                long c0) {
+  u64 C[ALPHA], Cs[ALPHA];
+  C[0] = P.Rm;
+  Cs[0] = P.Rm_s;
+  const u64* le = a.lenter2 + 2 * (G.lenter_off + g);
+#pragma unroll
+  for (int k = 1; k < ALPHA; ++k) {
+    C[k] = le[0];
+    Cs[k] = le[1];
+    le += 2 * nP;
+  }
+  const i64* base = a.src.row(bt, G.first_row) + c0;
+#pragma unroll
+  for (int h = 0; h < 16; h += 4) {
+    i64 d[4][ALPHA];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < ALPHA; ++k) d[i][k] = base[(long)k * a.src.rs + ((long)tb::tile_x(tr, h + i, f0) << LB)];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      u64 v = tb::shoup((u64)(d[i][0] + (i64)P.off), C[0], Cs[0], P.q);
+#pragma unroll
+      for (int k = 1; k < ALPHA; ++k) {
+        v += tb::shoup((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
+        if (!P.small) v = (v >= P.q2) ? v - P.q2 : v;
+      }
+      x[h + i] = (i64)v;
     }
-    return (i64)x;
   }
 }
 
 // forward pass A with a fused prologue.  EXTEND: grid.z = batch * ngroups, dst batch index = grid.z.
 template <int LA, int PRO>
-__global__ void __launch_bounds__(256) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
+__global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int W = 1 << a.LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> a.LW;
@@ -69,9 +95,21 @@ __global__ void __launch_bounds__(256) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   i64* d = a.dst.row(blockIdx.z, limb) + c0;
   constexpr int f0 = tb::fwd_field<LA>(0);
   i64 x[16];
+  if constexpr (PRO == TB_FPRO_EXTEND) {
+    const TbKsGroup& G = a.lv->g[gi];
+    switch (G.alpha) {
+#define XCASE(n) \
+  case n:        \
+    extend_prologue<n>(x, a, P, G, bt, g, c.P, tr, f0, c.LB, c0); \
+    break;
+      XCASE(1) XCASE(2) XCASE(3) XCASE(4) XCASE(5) XCASE(6) XCASE(7) XCASE(8)
+#undef XCASE
+    }
+  } else {
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((long)tb::tile_x(tr, i, f0) << c.LB) + c0, g, c.P);
+    for (int i = 0; i < 16; ++i)
+      x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((long)tb::tile_x(tr, i, f0) << c.LB) + c0, g, c.P);
+  }
   auto slot = [&](int lx) { return tb::pad16((lx << a.LW) | col); };
   const TbTw2* tw = c.tw + ((long)g << c.logN);
   if (P.small)
@@ -84,7 +122,7 @@ __global__ void __launch_bounds__(256) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
 
 // forward pass B; outputs: small primes < 38q, other primes reduced to [0, 2q).
 template <int LB>
-__global__ void __launch_bounds__(256) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst, int prime0) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -97,11 +135,9 @@ __global__ void __launch_bounds__(256) k_fast_fwd_B(TbDevFast c, TbView src, TbV
   auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
   constexpr int f0 = tb::fwd_field<LB>(0);
   i64 x[16];
+  // round-0 layout: 16 consecutive threads read 16 consecutive residues (one 128-byte line)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) sm[tb::pad16(i * nt + tid)] = s[i * nt + tid];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
+  for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
   const TbTw2* tw = c.tw + ((long)g << c.logN);
   if (P.small) {
     tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
@@ -110,17 +146,20 @@ __global__ void __launch_bounds__(256) k_fast_fwd_B(TbDevFast c, TbView src, TbV
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
   }
-  __syncthreads();
+  // final layout (field 0): a thread owns 16 consecutive residues -> eight 128-bit stores
+  longlong2* dv = reinterpret_cast<longlong2*>(d + ((blk << LB) | (lt << 4)));
 #pragma unroll
-  for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) d[i * nt + tid] = sm[tb::pad16(i * nt + tid)];
+  for (int i = 0; i < 8; ++i) {
+    longlong2 v;
+    v.x = x[2 * i];
+    v.y = x[2 * i + 1];
+    dv[i] = v;
+  }
 }
 
 // inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
 template <int LB>
-__global__ void __launch_bounds__(256) k_fast_inv_B(TbDevFast c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst, int prime0) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -133,30 +172,25 @@ __global__ void __launch_bounds__(256) k_fast_inv_B(TbDevFast c, TbView src, TbV
   auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
   constexpr int f0 = tb::fwd_field<LB>(0);
   i64 x[16];
+  const longlong2* sv = reinterpret_cast<const longlong2*>(s + ((blk << LB) | (lt << 4)));
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const i64 v = s[i * nt + tid];
-    sm[tb::pad16(i * nt + tid)] = v < 0 ? v + (i64)P.q2 : v;
+  for (int i = 0; i < 8; ++i) {
+    const longlong2 v = sv[i];
+    x[2 * i] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
+    x[2 * i + 1] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
   }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
   const TbTw2* tw = c.itw + ((long)g << c.logN);
   if (P.small)
     tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
   else
     tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
-  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, f0))] = x[i];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) d[i * nt + tid] = sm[tb::pad16(i * nt + tid)];
+  for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = x[i];
 }
 
 // inverse pass A' + exit: y = CS1(x * N^-1 R^-1)  == intt_radix2_exit_reduce of the reference (canonical).
 template <int LA>
-__global__ void __launch_bounds__(256) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LW) {
+__global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LW) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
@@ -199,11 +233,13 @@ __device__ __forceinline__ i64 tb_norm2q(i64 x, i64 q2) {
 // key inner product, mod q: small primes accumulate the 128-bit products over the digit groups and
 // reduce once; other primes reduce per term.  Output lazy residues in [0, 2q + small).
 __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
-                                                  const i64* ext, i64* acc, int level, int N, int rowsE) {
-  const int t = blockIdx.y, bt = blockIdx.z;
+                                                  const i64* ext, i64* acc, int level, int N, int rowsE, int nb) {
+  // grid.x = nb * tiles with the batch index fastest: the nb ciphertexts of a chunk read the same key
+  // tile back to back, so the key is fetched from HBM once per chunk (L2 serves the rest)
+  const int t = blockIdx.y, bt = blockIdx.x % nb;
   const TbPrime& P = c.pr[level + t];
   const int small = f.fp[level + t].small;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int j = ((blockIdx.x / nb) * blockDim.x + threadIdx.x) * 2;
   if (j >= N) return;
   const int ng = lv->ngroups;
   longlong2 o0, o1;
@@ -242,4 +278,48 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
   }
   *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 0) * rowsE + t) * N + j) = o0;
   *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 1) * rowsE + t) * N + j) = o1;
+}
+
+// ModDown, mod q (he_fused_cuda.cu:471-519 composes x <- (x - p_k) P_k^-1 for k = K-1..0; expanded:
+// x = c B_{K-1} - sum_k p_k B_k with B_k = prod_{j<=k} P_j^-1).  The special limbs p_k are the exact
+// integers produced by the chain-backward step (representative-sensitive, kept exact); the result is
+// canonical, hence identical to the reference's.  bn: [(K+1)][P][2] = (-B_k mod q, Shoup) for k < K,
+// then (B_{K-1}, Shoup).  TAIL as in k_divide_by_p.
+template <int TAIL>
+__global__ void __launch_bounds__(256) k_fast_divide_by_p(TbDevFast f, TbView cc, TbView p, TbView add, TbView out,
+                                                          const u64* bn, int K, int prime0, int N) {
+  const int r = blockIdx.y, bt = blockIdx.z;
+  const int g = prime0 + r;
+  const TbFastPrime P = f.fp[g];
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (j >= N) return;
+  const u64* b = bn + 2 * g;
+  const longlong2 cv = *reinterpret_cast<const longlong2*>(cc.row(bt, r) + j);
+  const u64* bk = b + 2 * (long)K * f.P;
+  u64 x0 = tb::shoup((u64)(cv.x + (i64)P.q), bk[0], bk[1], P.q);
+  u64 x1 = tb::shoup((u64)(cv.y + (i64)P.q), bk[0], bk[1], P.q);
+  for (int k = 0; k < K; ++k) {
+    const longlong2 pv = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
+    const u64* bb = b + 2 * (long)k * f.P;
+    x0 += tb::shoup((u64)(pv.x + (i64)P.off), bb[0], bb[1], P.q);
+    x1 += tb::shoup((u64)(pv.y + (i64)P.off), bb[0], bb[1], P.q);
+    x0 = (x0 >= P.q2) ? x0 - P.q2 : x0;
+    x1 = (x1 >= P.q2) ? x1 - P.q2 : x1;
+  }
+  i64 y0 = (i64)(x0 >= P.q ? x0 - P.q : x0);
+  i64 y1 = (i64)(x1 >= P.q ? x1 - P.q : x1);
+  if constexpr (TAIL != 0) {
+    const longlong2 av = *reinterpret_cast<const longlong2*>(add.row(bt, r) + j);
+    if constexpr (TAIL == 1) {
+      y0 = tb_cs1(av.x + y0, (i64)P.q);
+      y1 = tb_cs1(av.y + y1, (i64)P.q);
+    } else {
+      y0 = tb_cs1(tb_add(av.x, y0, (i64)P.q2), (i64)P.q);
+      y1 = tb_cs1(tb_add(av.y, y1, (i64)P.q2), (i64)P.q);
+    }
+  }
+  longlong2 o;
+  o.x = y0;
+  o.y = y1;
+  *reinterpret_cast<longlong2*>(out.row(bt, r) + j) = o;
 }
