@@ -282,25 +282,86 @@ def run_ours(args):
             roof["traffic"] = json.load(f).get(roof["kernel"])
 
     # ---- end to end: host (pinned) buffers -> C ABI -> host result, copies inside the timed region --
+    # The batch is cut in sub-batches that flow through three streams (H2D, compute, D2H) with two
+    # device slots each, so PCIe transfers of sub-batch i+1 / i-1 overlap the kernels of sub-batch i.
     Be = min(B, args.e2e_batch)
+    sb = min(Be, args.e2e_sub)
+    nsub = Be // sb
+    Be = nsub * sb
     hin = [torch.empty(Be, no, N, dtype=torch.int64).pin_memory() for _ in range(4)]
     for hbuf, src in zip(hin, (a0, a1, b0, b1)):
         hbuf.copy_(src[:Be])
     hout = [torch.empty(Be, L, N, dtype=torch.int64).pin_memory() for _ in range(2)]
-    din = [t[:Be] for t in (a0, a1, b0, b1)]
-    dout = [out0[:Be], out1[:Be]]
+    din = [[t[k * sb:(k + 1) * sb] for t in (a0, a1, b0, b1)] for k in range(2)]      # two input slots
+    dout = [[out0[k * sb:(k + 1) * sb], out1[k * sb:(k + 1) * sb]] for k in range(2)]  # two output slots
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
     def e2e_step():
-        for d, h_ in zip(din, hin):
-            d.copy_(h_, non_blocking=True)
-        ctx.cc_mult_relin(0, din[0], din[1], din[2], din[3], evk, dout[0], dout[1], True)
-        for h_, d in zip(hout, dout):
-            h_.copy_(d, non_blocking=True)
+        ev_cmp, ev_out = [None, None], [None, None]
+        for i in range(nsub):
+            k = i % 2
+            with torch.cuda.stream(s_in):
+                if ev_cmp[k] is not None:
+                    s_in.wait_event(ev_cmp[k])          # slot's previous inputs consumed
+                for d, h_ in zip(din[k], hin):
+                    d.copy_(h_[i * sb:(i + 1) * sb], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in)
+                if ev_out[k] is not None:
+                    s_cmp.wait_event(ev_out[k])         # slot's previous outputs copied out
+                ctx.cc_mult_relin(0, din[k][0], din[k][1], din[k][2], din[k][3], evk, dout[k][0], dout[k][1], True)
+                ev_cmp[k] = torch.cuda.Event()
+                ev_cmp[k].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp[k])
+                for h_, d in zip(hout, dout[k]):
+                    h_[i * sb:(i + 1) * sb].copy_(d, non_blocking=True)
+                ev_out[k] = torch.cuda.Event()
+                ev_out[k].record(s_out)
 
-    ms_e2e = timed(e2e_step, args.steps, 1)
+    def e2e_timed(steps, warmup):
+        cur = torch.cuda.current_stream()
+        for _ in range(warmup):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cur)
+        for st_ in (s_in, s_cmp, s_out):
+            st_.wait_event(e0)
+        for _ in range(steps):
+            e2e_step()
+        for st_ in (s_in, s_cmp, s_out):
+            ev = torch.cuda.Event()
+            ev.record(st_)
+            cur.wait_event(ev)
+        e1.record(cur)
+        barrier()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        return ms_
+
+    ms_e2e = e2e_timed(args.steps, 1)
     e2e = {"value": world * Be * args.steps / (ms_e2e / 1e3), "unit": UNIT,
            "h2d_bytes_per_step": 4 * Be * no * N * 8, "d2h_bytes_per_step": 2 * Be * L * N * 8,
-           "batch": Be, "ms_per_step": ms_e2e / args.steps}
+           "batch": Be, "sub_batch": sb, "ms_per_step": ms_e2e / args.steps,
+           "pcie_gbs": (4 * Be * no + 2 * Be * L) * N * 8 * args.steps / (ms_e2e / 1e3) / 1e9,
+           "note": "pinned host buffers; H2D / kernels / D2H pipelined over 3 streams (PCIe-bound)"}
+
+    ref_ext = None
+    if rank == 0 and world == 1 and not args.no_reference_ext and not args.quick:
+        # baseline (b) of the north star: the reference's own CUDA extension on this GPU (separate process)
+        try:
+            pr = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "bench_reference_ext.py"), "--iters", "10",
+                                 "--warmup", "3"], capture_output=True, text=True, timeout=600)
+            last = [ln for ln in pr.stdout.splitlines() if ln.startswith("{")]
+            ref_ext = json.loads(last[-1]) if last else {"unavailable": (pr.stderr or "no output")[-300:]}
+        except Exception as exc:  # noqa: BLE001
+            ref_ext = {"unavailable": repr(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -319,7 +380,7 @@ def run_ours(args):
                        "sharding": "ciphertext batch, no data-path collective",
                        "l2": "inputs (>= 17 GiB per step at batch 256) exceed the 126 MB L2"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-            "cpu_baseline": cpu, "kernel_time_share": shares, "kernel_us_per_op": kernel_us_per_op,
+            "cpu_baseline": cpu, "reference_cuda_ext": ref_ext, "kernel_time_share": shares, "kernel_us_per_op": kernel_us_per_op,
             "hmult_hbm_roofline": {"algorithmic_bytes_per_op": alg_bytes, "roofline_ops_per_s": peak * 1e9 / alg_bytes,
                                    "frac": value / world / (peak * 1e9 / alg_bytes)},
             "extra": extra,
@@ -335,10 +396,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="ciphertext pairs per GPU per step")
-    ap.add_argument("--chunk", type=int, default=4, help="ciphertexts per internal pass (workspace size)")
-    ap.add_argument("--e2e-batch", type=int, default=32)
+    ap.add_argument("--chunk", type=int, default=16, help="ciphertexts per internal pass (workspace size)")
+    ap.add_argument("--e2e-batch", type=int, default=64)
+    ap.add_argument("--e2e-sub", type=int, default=8, help="sub-batch of the end-to-end pipeline")
+    ap.add_argument("--no-reference-ext", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--quick", action="store_true", help="skip the secondary rotate / NTT figures")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary rotate / NTT figures and the reference ext")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
