@@ -58,6 +58,14 @@ typedef struct {
  *      constant_mem_context.py:126-295; no 64-prime cap, not process-global) ------------------- */
 tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int num_special,
                             const int64_t* q /*[num_primes]*/, int scale_bits);
+/* RNS-limb sharding (BASELINE.json configs[3]): the context of `rank` holds the ordinary
+ * primes of the digit groups that rank owns (rns_partition.py:34-52: scale group g -> rank (np-1-g) mod
+ * world, base prime -> rank 0) followed by the replicated special primes; tensors passed to it hold the
+ * corresponding LOCAL rows.  Such a context supports the op layer and tb200_ks_digits / tb200_ks_finish. */
+tb200_ctx* tb200_ctx_create_sharded(int device, int logN, int num_primes, int num_special, const int64_t* q,
+                                    int scale_bits, int rank, int world);
+/* global prime index of every local row [num_local_primes] */
+int tb200_ctx_local_primes(const tb200_ctx*, int32_t* out);
 void tb200_ctx_destroy(tb200_ctx*);
 const char* tb200_last_error(void);
 const char* tb200_version(void);
@@ -142,6 +150,21 @@ int tb200_rescale(tb200_ctx*, int level, int batch, const tb200_poly* in0, const
 /* create_switcher :1201-1363 on a coefficient-domain canonical polynomial a [L][N] at `level`. */
 int tb200_keyswitch(tb200_ctx*, int level, int batch, const tb200_poly* a, const tb200_ksk* ksk,
                     const tb200_poly* out0, const tb200_poly* out1, tb200_stream);
+/* Key switch in two halves, the seam where limb-sharded ranks exchange the ModUp digits:
+ *   tb200_ks_state_info: out[4] = {rows of the digit-state buffer, first row of this rank's segment,
+ *                        rows per segment, local ordinary rows L at this level};
+ *   tb200_ks_digits: mixed-radix digits (ckks_engine.py:889-921) of the digit groups this rank owns,
+ *                    written into its segment of `state` [state_rows][N] (a: local rows, canonical);
+ *   -- sharded: ONE in-place all-gather of the segments (ncclAllGather over NVLink) --
+ *   tb200_ks_finish: extend to the local ordinary + special limbs, NTT, key inner product with the
+ *                    local key rows, inverse NTT, ModDown; tail 0: out = (ks0, ks1); 1: out = CS1(add +
+ *                    ks) for both (relinearize); 2: out0 = CS1(CS2(add0 + ks0)), out1 = ks1 (switch_key).
+ * On an unsharded context digits + finish == tb200_keyswitch. */
+int tb200_ks_state_info(const tb200_ctx*, int level, int32_t* out);
+int tb200_ks_digits(tb200_ctx*, int level, int batch, const tb200_poly* a, const tb200_poly* state, tb200_stream);
+int tb200_ks_finish(tb200_ctx*, int level, int batch, const tb200_poly* state, const tb200_ksk* ksk,
+                    const tb200_poly* add0, const tb200_poly* add1, const tb200_poly* out0, const tb200_poly* out1,
+                    int tail, tb200_stream);
 /* cc_mult (+relinearize) :1640-1732.  a*, b*: [L_in][N] at `level`; with pre_rescale the product
  * lives at level+1 and has L_in-1 rows.  out0/out1 canonical coefficient domain. */
 int tb200_cc_mult_relin(tb200_ctx*, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,

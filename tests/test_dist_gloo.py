@@ -57,3 +57,53 @@ def _free_port():
 @pytest.mark.parametrize("total", [5, 8])
 def test_two_rank_batch_sharding_gloo(total):
     mp.spawn(_worker, args=(2, _free_port(), total), nprocs=2, join=True)
+
+
+def _sharded_ks_worker(rank, world, port, seed):
+    """Runs the real limb-sharded key-switch orchestration (dist.LimbShardedKeySwitch) with gloo on CPU
+    tensors; the kernels are the host-compiled sources of tests/emu (no GPU in this container)."""
+    import subprocess
+
+    import numpy as np
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        so = os.path.join(root, "tests", "emu", "_build", "libtb200_emu.so")
+        if not os.path.exists(so):
+            subprocess.run(["sh", os.path.join(root, "tests", "emu", "build_emu.sh")], check=True, capture_output=True)
+        from oracle.context import OracleContext, toy_primes
+        from oracle.engine import OracleEngine
+        from tiberate_fhe_b200 import _native
+        from tiberate_fhe_b200.context import KeySwitchKeyView, Tb200Context
+        from tiberate_fhe_b200.dist import LimbShardedKeySwitch, shard_rows
+
+        logN, ns, K = 8, 5, 2
+        q = toy_primes(logN, ns, K)
+        octx = OracleContext(logN, q, K)
+        eng = OracleEngine(octx)
+        rng = np.random.default_rng(seed)  # same stream on every rank
+        sk, _ = eng.gen_secret(rng)
+        evk = eng.gen_evk(rng, sk)
+        ctx = Tb200Context(logN, q, K, lib=_native.Lib(so), rank=rank, world=world)
+        ks = LimbShardedKeySwitch(ctx)
+        ids = ctx.local_prime_ids
+        key = KeySwitchKeyView([None if p is None else (torch.from_numpy(np.ascontiguousarray(p[0][ids])),
+                                                        torch.from_numpy(np.ascontiguousarray(p[1][ids]))) for p in evk],
+                               octx.N)
+        for level in (0, 2):
+            a = eng.uniform(rng, octx.level_primes(level, False))
+            want0, want1 = eng.create_switcher(a, evk, level)
+            a_loc = shard_rows(torch.from_numpy(a), ctx, level)
+            o0, o1 = torch.zeros_like(a_loc), torch.zeros_like(a_loc)
+            ks(level, a_loc, key, o0, o1)
+            rows = [g - level for g in ctx.local_rows(level)]
+            assert np.array_equal(o0.numpy(), want0[rows]) and np.array_equal(o1.numpy(), want1[rows]), (rank, level)
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_limb_sharded_keyswitch_two_ranks_gloo():
+    mp.spawn(_sharded_ks_worker, args=(2, _free_port(), 5), nprocs=2, join=True)

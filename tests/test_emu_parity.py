@@ -98,3 +98,67 @@ def test_bad_arguments_raise(h):
             s.ctx.rotate(0, 4, a, a, None, a.copy(), a.copy())  # even galois element
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_limb_sharded_keyswitch_matches_single_device(h, world):
+    """BASELINE configs[3] logic on toy rings: every rank computes the ModUp digits of the digit groups
+    it owns, the digit-state segments are all-gathered (emulated here by copies), each rank finishes
+    the key switch for its own limbs; the assembled result equals the single-device oracle."""
+    import numpy as np
+
+    from oracle.context import OracleContext, toy_primes
+    from oracle.engine import OracleEngine
+    from tiberate_fhe_b200.context import KeySwitchKeyView, Tb200Context
+
+    logN, ns, K = 8, 7, 2
+    q = toy_primes(logN, ns, K)
+    octx = OracleContext(logN, q, K)
+    eng = OracleEngine(octx)
+    rng = np.random.default_rng(world)
+    N = octx.N
+    sk, _ = eng.gen_secret(rng)
+    evk = eng.gen_evk(rng, sk)
+    ctxs = [Tb200Context(logN, q, K, lib=h.lib, rank=r, world=world) for r in range(world)]
+    try:
+        owned = sorted(g for c in ctxs for g in c.local_prime_ids[: c.num_ordinary])
+        assert owned == list(range(octx.num_ordinary)), "every ordinary prime has exactly one owner"
+        for level in (0, 1, 3, 6):
+            lp = octx.level_primes(level, False)
+            a = eng.uniform(rng, lp)
+            add = eng.uniform(rng, lp)
+            want0, want1 = eng.create_switcher(a, evk, level)
+            want_sw = eng.switch_key([add, a], evk, level)
+            states, infos = [], []
+            for c in ctxs:
+                S, row0, seg, Lloc = c.ks_state_info(level)
+                rows = [g - level for g in c.local_rows(level)]
+                assert Lloc == len(rows)
+                st = np.zeros((S, N), dtype=np.int64)
+                a_loc = np.ascontiguousarray(a[rows]) if rows else np.zeros((1, N), dtype=np.int64)
+                c.ks_digits(level, a_loc, st)
+                states.append(st)
+                infos.append((row0, seg, rows))
+            for r, (row0, seg, _) in enumerate(infos):  # the all-gather
+                for st in states:
+                    st[row0:row0 + seg] = states[r][row0:row0 + seg]
+            got0 = np.zeros_like(want0)
+            got1 = np.zeros_like(want1)
+            sw0 = np.zeros_like(want0)
+            for c, st, (_, _, rows) in zip(ctxs, states, infos):
+                if not rows:
+                    continue
+                ids = c.local_prime_ids
+                key = KeySwitchKeyView([None if p is None else (np.ascontiguousarray(p[0][ids]),
+                                                                np.ascontiguousarray(p[1][ids])) for p in evk], N)
+                o0 = np.zeros((len(rows), N), dtype=np.int64)
+                o1 = np.zeros_like(o0)
+                c.ks_finish(level, st, key, o0, o1)
+                got0[rows], got1[rows] = o0, o1
+                c.ks_finish(level, st, key, o0, o1, add0=np.ascontiguousarray(add[rows]), tail=2)
+                sw0[rows] = o0
+            assert np.array_equal(got0, want0) and np.array_equal(got1, want1), f"level {level}"
+            assert np.array_equal(sw0, want_sw[0]), f"switch_key tail, level {level}"
+    finally:
+        for c in ctxs:
+            c.close()

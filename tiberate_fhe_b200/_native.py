@@ -41,6 +41,8 @@ _i, _i64, _vp = C.c_int, C.c_int64, C.c_void_p
 # name -> (restype, argtypes); every symbol declared in include/tb200.h
 SIGNATURES = {
     "tb200_ctx_create": (_vp, [_i, _i, _i, _i, _vp, _i]),
+    "tb200_ctx_create_sharded": (_vp, [_i, _i, _i, _i, _vp, _i, _i, _i]),
+    "tb200_ctx_local_primes": (_i, [_vp, _vp]),
     "tb200_ctx_destroy": (None, [_vp]),
     "tb200_last_error": (C.c_char_p, []),
     "tb200_version": (C.c_char_p, []),
@@ -59,6 +61,9 @@ SIGNATURES = {
     "tb200_divide_by_p": (_i, [_vp, _i, PP, PP, PP, _vp]),
     "tb200_rescale": (_i, [_vp, _i, _i, PP, PP, PP, PP, _i, _vp]),
     "tb200_keyswitch": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, _vp]),
+    "tb200_ks_state_info": (_i, [_vp, _i, _vp]),
+    "tb200_ks_digits": (_i, [_vp, _i, _i, PP, PP, _vp]),
+    "tb200_ks_finish": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_mult_relin": (_i, [_vp, _i, _i, PP, PP, PP, PP, C.POINTER(Ksk), PP, PP, _i, _vp]),
     "tb200_cc_mult_triplet": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_relinearize": (_i, [_vp, _i, _i, PP, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),

@@ -64,7 +64,7 @@ def poly(x, N: int, batched: bool | None = None) -> Poly:
 
 
 def _stream(x) -> int:
-    if isinstance(x, np.ndarray):
+    if isinstance(x, np.ndarray) or not x.is_cuda:
         return 0
     import torch
 
@@ -100,8 +100,12 @@ class KeySwitchKeyView:
 class Tb200Context:
     """One per (parameter set, GPU).  `lib` defaults to the CUDA library (fails loudly if absent)."""
 
-    def __init__(self, logN: int, q, num_special: int, scale_bits: int = 40, device: int = 0, lib=None):
+    def __init__(self, logN: int, q, num_special: int, scale_bits: int = 40, device: int = 0, lib=None,
+                 rank: int = 0, world: int = 1):
+        """`q` is always the GLOBAL prime chain.  With world > 1 the context is limb-sharded: it holds the
+        ordinary primes of the digit groups `rank` owns plus the special primes (see include/tb200.h)."""
         self.lib = lib if lib is not None else _native.get_lib()
+        self.rank, self.world = int(rank), int(world)
         self.logN, self.N = int(logN), 1 << int(logN)
         self.q = [int(x) for x in q]
         self.P, self.K = len(self.q), int(num_special)
@@ -110,13 +114,27 @@ class Tb200Context:
         self.scale_bits = int(scale_bits)
         self.device = int(device)
         qa = np.ascontiguousarray(self.q, dtype=np.int64)
-        h = self.lib.tb200_ctx_create(self.device, self.logN, self.P, self.K, qa.ctypes.data, self.scale_bits)
+        if self.world == 1:
+            h = self.lib.tb200_ctx_create(self.device, self.logN, self.P, self.K, qa.ctypes.data, self.scale_bits)
+        else:
+            h = self.lib.tb200_ctx_create_sharded(self.device, self.logN, self.P, self.K, qa.ctypes.data,
+                                                  self.scale_bits, self.rank, self.world)
         if not h:
             raise Tb200Error("tb200_ctx_create failed: " + self.lib.tb200_last_error().decode(errors="replace"))
         self.h = C.c_void_p(h)
         info = (C.c_int32 * 8)()
         self.lib.check(self.lib.tb200_ctx_info(self.h, info), "ctx_info")
         self.LA, self.LB, self.num_groups0 = info[4], info[5], info[7]
+        self.P_global, self.q_global = self.P, list(self.q)
+        if self.world > 1:  # from here on P / q / num_ordinary describe the LOCAL rows
+            self.P = info[2]
+            ids = (C.c_int32 * self.P)()
+            self.lib.check(self.lib.tb200_ctx_local_primes(self.h, ids), "local_primes")
+            self.local_prime_ids = list(ids)
+            self.q = [self.q_global[i] for i in self.local_prime_ids]
+            self.num_ordinary = self.P - self.K
+        else:
+            self.local_prime_ids = list(range(self.P))
         # host mirror of the Montgomery constants (mont_context.py:26-57) for callers that need them
         self.k = [(R * pow(R, -1, qi) - 1) // qi for qi in self.q]
         self.Rs = [R * R % qi for qi in self.q]
@@ -243,6 +261,28 @@ class Tb200Context:
         rc = self.lib.tb200_keyswitch(self.h, level, self._batch(a), self._pp(a), C.byref(ksk.c), self._pp(out0),
                                       self._pp(out1), _stream(out0))
         self.lib.check(rc, "keyswitch")
+
+    # ---- key switch in two halves (the seam for limb sharding) ---------------------------------
+    def ks_state_info(self, level: int):
+        """(state_rows, segment_row0, segment_rows, local_ordinary_rows) at `level`."""
+        out = (C.c_int32 * 4)()
+        self.lib.check(self.lib.tb200_ks_state_info(self.h, level, out), "ks_state_info")
+        return tuple(out)
+
+    def local_rows(self, level: int, with_special: bool = False):
+        """Global prime ids of the local rows alive at `level`."""
+        ids = [g for g in self.local_prime_ids[: self.num_ordinary] if g >= level]
+        return ids + (self.local_prime_ids[self.num_ordinary:] if with_special else [])
+
+    def ks_digits(self, level: int, a, state):
+        rc = self.lib.tb200_ks_digits(self.h, level, self._batch(state), self._pp(a), self._pp(state), _stream(state))
+        self.lib.check(rc, "ks_digits")
+
+    def ks_finish(self, level: int, state, ksk: KeySwitchKeyView, out0, out1, add0=None, add1=None, tail: int = 0):
+        rc = self.lib.tb200_ks_finish(self.h, level, self._batch(state), self._pp(state), C.byref(ksk.c),
+                                      self._pp(add0), self._pp(add1), self._pp(out0), self._pp(out1), int(tail),
+                                      _stream(out0))
+        self.lib.check(rc, "ks_finish")
 
     def cc_mult_relin(self, level: int, a0, a1, b0, b1, evk: KeySwitchKeyView, out0, out1, pre_rescale: bool = True):
         rc = self.lib.tb200_cc_mult_relin(self.h, level, self._batch(a0), self._pp(a0), self._pp(a1), self._pp(b0),

@@ -134,25 +134,44 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   delete c;
 }
 
-extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int num_special, const int64_t* q,
-                                       int scale_bits) {
-  if (logN < 8 || logN > 17 || num_special < 1 || num_special > TB_MAXA || num_primes < num_special + 1 || !q) {
+// Ownership of the ordinary primes when a ring is sharded by RNS limb over `world` ranks
+// (tiberate/context/rns_partition.py:34-52): scale-prime group g (K consecutive primes) belongs to
+// rank (np-1-g) mod world, the base prime to rank 0; the special primes are replicated.
+static int tb_group_owner(int gid, int np, int world) { return gid < np ? (np - 1 - gid) % world : 0; }
+
+static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special, const int64_t* qg, int scale_bits,
+                                  int rank, int world) {
+  if (logN < 8 || logN > 17 || num_special < 1 || num_special > TB_MAXA || Pg < num_special + 1 || !qg) {
     fail(TB200_EINVAL, "ctx_create: need 8 <= logN <= 17, 1 <= K <= %d, P >= K+1", TB_MAXA);
     return nullptr;
   }
-  const int N = 1 << logN, P = num_primes, K = num_special, no = P - K, ns = no - 1;
+  if (world < 1 || rank < 0 || rank >= world) {
+    fail(TB200_EINVAL, "ctx_create: bad rank %d / world %d", rank, world);
+    return nullptr;
+  }
+  const int N = 1 << logN, K = num_special, no_g = Pg - K, ns = no_g - 1;
   const int np = (ns + K - 1) / K;  // scale-prime groups; + 1 base group
   if (np + 1 > TB_MAXG) {
     fail(TB200_EINVAL, "ctx_create: %d digit groups exceed TB200_MAX_GROUPS", np + 1);
     return nullptr;
   }
-  for (int g = 0; g < P; ++g) {
-    const u64 qi = (u64)q[g];
-    if (q[g] <= 2 || (qi - 1) % (2ull * N) != 0 || (qi >> 60) > 0) {
-      fail(TB200_EINVAL, "ctx_create: prime %d (%lld) must be = 1 mod 2N and < 2^60", g, (long long)q[g]);
+  for (int g = 0; g < Pg; ++g) {
+    const u64 qi = (u64)qg[g];
+    if (qg[g] <= 2 || (qi - 1) % (2ull * N) != 0 || (qi >> 60) > 0) {
+      fail(TB200_EINVAL, "ctx_create: prime %d (%lld) must be = 1 mod 2N and < 2^60", g, (long long)qg[g]);
       return nullptr;
     }
   }
+  // local prime list: owned ordinary primes (ascending global id) followed by the special primes
+  auto group_of = [&](int p) { return p < ns ? p / K : np; };
+  std::vector<int> ord_gid;
+  for (int p = 0; p < no_g; ++p)
+    if (tb_group_owner(group_of(p), np, world) == rank) ord_gid.push_back(p);
+  std::vector<int64_t> qloc;
+  for (int p : ord_gid) qloc.push_back(qg[p]);
+  for (int kk = 0; kk < K; ++kk) qloc.push_back(qg[no_g + kk]);
+  const int64_t* q = qloc.data();
+  const int no = (int)ord_gid.size(), P = no + K;
   if (cudaSetDevice(device) != cudaSuccess) {
     fail(TB200_ENODEV, "ctx_create: cudaSetDevice(%d) failed", device);
     return nullptr;
@@ -164,7 +183,17 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
   c->P = P;
   c->K = K;
   c->num_ord = no;
-  c->num_levels = no;
+  c->num_levels = no_g;
+  c->rank = rank;
+  c->world = world;
+  c->ord_gid = ord_gid;
+  c->qg.assign(qg, qg + Pg);
+  c->lstart.resize(no_g + 1);
+  for (int l = 0; l <= no_g; ++l) {
+    int n = 0;
+    for (int p : ord_gid) n += p < l ? 1 : 0;
+    c->lstart[l] = n;
+  }
   c->scale_bits = scale_bits;
   c->LB = logN >= 12 ? 8 : logN / 2;
   c->LA = logN - c->LB;
@@ -234,51 +263,67 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
     }
   }
   // rescale scales and P_k^-1 tables
-  std::vector<i64> resc((size_t)no * P, 0), pir((size_t)K * P, 0), pirsp((size_t)K * K, 0);
-  for (int l = 0; l < no; ++l)
-    for (int g = l + 1; g < no; ++g) {
-      const u64 qg = (u64)q[g], Rm = (u64)(Rbig % qg);
-      resc[(size_t)l * P + g] = (i64)h_mulmod(h_invmod_prime((u64)q[l] % qg, qg), Rm, qg);
+  std::vector<i64> resc((size_t)no_g * P, 0), pir((size_t)K * P, 0), pirsp((size_t)K * K, 0);
+  for (int l = 0; l < no_g; ++l)
+    for (int g = 0; g < no; ++g) {
+      if (ord_gid[g] <= l) continue;
+      const u64 qq = (u64)q[g], Rm = (u64)(Rbig % qq);
+      resc[(size_t)l * P + g] = (i64)h_mulmod(h_invmod_prime((u64)qg[l] % qq, qq), Rm, qq);
     }
-  std::vector<u64> resc3((size_t)no * P * 3, 0);
-  for (int l = 0; l < no; ++l)
-    for (int g = l + 1; g < no; ++g) {
-      const u64 qg = (u64)q[g], ql = (u64)q[l], Rm = (u64)(Rbig % qg);
-      const u64 c1 = h_mulmod(h_invmod_prime(ql % qg, qg), Rm, qg);
+  std::vector<u64> resc3((size_t)no_g * P * 3, 0);
+  for (int l = 0; l < no_g; ++l)
+    for (int g = 0; g < no; ++g) {
+      if (ord_gid[g] <= l) continue;
+      const u64 qq = (u64)q[g], ql = (u64)qg[l], Rm = (u64)(Rbig % qq);
+      const u64 c1 = h_mulmod(h_invmod_prime(ql % qq, qq), Rm, qq);
       u64* r3 = &resc3[((size_t)l * P + g) * 3];
       r3[0] = c1;
-      r3[1] = h_shoup(c1, qg);
-      r3[2] = qg * ((ql + qg - 1) / qg + 1);  // multiple of q_g above q_l (+ q_g of slack for tiny negatives)
+      r3[1] = h_shoup(c1, qq);
+      r3[2] = qq * ((ql + qq - 1) / qq + 1);  // multiple of q_g above q_l (+ q_g of slack for tiny negatives)
     }
   for (int kk = 0; kk < K; ++kk)
     for (int g = 0; g < no + kk; ++g) {
-      const u64 qg = (u64)q[g], Rm = (u64)(Rbig % qg);
-      pir[(size_t)kk * P + g] = (i64)h_mulmod(h_invmod_prime((u64)q[no + kk] % qg, qg), Rm, qg);
+      const u64 qq = (u64)q[g], Rm = (u64)(Rbig % qq);
+      pir[(size_t)kk * P + g] = (i64)h_mulmod(h_invmod_prime((u64)q[no + kk] % qq, qq), Rm, qq);
     }
   for (int kk = 0; kk < K; ++kk)
     for (int row = 0; row < kk; ++row) pirsp[(size_t)kk * K + row] = pir[(size_t)kk * P + no + row];
   // ModDown in product form: B_k = prod_{j<=k} P_j^-1 mod q_g
   std::vector<u64> bn((size_t)(K + 1) * P * 2, 0);
   for (int g = 0; g < no; ++g) {
-    const u64 qg = (u64)q[g];
+    const u64 qq = (u64)q[g];
     u64 B = 1;
     for (int kk = 0; kk < K; ++kk) {
-      B = h_mulmod(B, h_invmod_prime((u64)q[no + kk] % qg, qg), qg);
-      const u64 neg = (qg - B) % qg;
+      B = h_mulmod(B, h_invmod_prime((u64)q[no + kk] % qq, qq), qq);
+      const u64 neg = (qq - B) % qq;
       bn[((size_t)kk * P + g) * 2] = neg;
-      bn[((size_t)kk * P + g) * 2 + 1] = h_shoup(neg, qg);
+      bn[((size_t)kk * P + g) * 2 + 1] = h_shoup(neg, qq);
     }
     bn[((size_t)K * P + g) * 2] = B;
-    bn[((size_t)K * P + g) * 2 + 1] = h_shoup(B, qg);
+    bn[((size_t)K * P + g) * 2 + 1] = h_shoup(B, qq);
   }
   // digit groups per level
   std::vector<i64> lenter;
   std::vector<u64> lenter2;
-  c->ks.resize(no);
-  for (int l = 0; l < no; ++l) {
+  c->ks.resize(no_g);
+  for (int l = 0; l < no_g; ++l) {
     TbKsLevel& lv = c->ks[l];
     memset(&lv, 0, sizeof(lv));
-    lv.L = no - l;
+    lv.L = no - c->lstart[l];
+    // rows of the digit-state buffer: owner-major, every rank's segment padded to the largest one, so
+    // that ONE in-place all-gather completes it (for world == 1: the global row order)
+    std::vector<int> owned_rows(world, 0);
+    for (int gid = 0; gid <= np; ++gid) {
+      const int lo = gid < np ? gid * K : ns;
+      const int hi = gid < np ? ((gid + 1) * K < ns ? (gid + 1) * K : ns) : ns + 1;
+      for (int p = lo; p < hi; ++p)
+        if (p >= l) owned_rows[tb_group_owner(gid, np, world)]++;
+    }
+    int seg = 0;
+    for (int r = 0; r < world; ++r) seg = owned_rows[r] > seg ? owned_rows[r] : seg;
+    lv.seg_rows = seg;
+    lv.state_rows = seg * world;
+    std::vector<int> fill(world, 0);
     for (int gid = 0; gid <= np; ++gid) {
       const int lo = gid < np ? gid * K : ns;
       const int hi = gid < np ? ((gid + 1) * K < ns ? (gid + 1) * K : ns) : ns + 1;
@@ -286,33 +331,45 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
       for (int p = lo; p < hi; ++p)
         if (p >= l) alive.push_back(p);
       if (alive.empty()) continue;
-      TbKsGroup& G = lv.g[lv.ngroups++];
+      const int owner = tb_group_owner(gid, np, world);
+      TbKsGroup& G = lv.g[lv.ngroups];
       const int alpha = (int)alive.size();
       G.alpha = alpha;
-      G.first_row = alive[0] - l;
       G.gid = gid;
+      G.state_row0 = owner * seg + fill[owner];
+      fill[owner] += alpha;
+      G.src_prime0 = -1;
+      G.src_row0 = -1;
+      if (owner == rank) {
+        int li = 0;
+        while (ord_gid[li] != alive[0]) ++li;
+        G.src_prime0 = li;
+        G.src_row0 = li - c->lstart[l];
+        lv.own[lv.nown++] = lv.ngroups;
+      }
+      lv.ngroups++;
       G.lenter_off = (long)lenter.size();
       // L_i = m_0 ... m_i reduced modulo whatever prime is needed
       auto Lmod = [&](int i, u64 m) {
         u64 r = 1 % m;
-        for (int t = 0; t <= i; ++t) r = h_mulmod(r, (u64)q[alive[t]] % m, m);
+        for (int t = 0; t <= i; ++t) r = h_mulmod(r, (u64)qg[alive[t]] % m, m);
         return r;
       };
       for (int i = 0; i + 1 < alpha; ++i) {
-        const u64 m1 = (u64)q[alive[i + 1]];
+        const u64 m1 = (u64)qg[alive[i + 1]];
         G.Y[i] = (i64)h_mulmod(h_invmod_prime(Lmod(i, m1), m1), (u64)(Rbig % m1), m1);
         for (int j = i + 2; j < alpha; ++j) {
-          const u64 mj = (u64)q[alive[j]];
+          const u64 mj = (u64)qg[alive[j]];
           G.Lsc[i][j] = (i64)h_mulmod(Lmod(i, mj), (u64)(Rbig % mj), mj);
         }
       }
       for (int i = 0; i + 1 < alpha; ++i)
         for (int g = 0; g < P; ++g) {
-          const u64 qg = (u64)q[g];
-          lenter.push_back((i64)h_mulmod(Lmod(i, qg), (u64)c->primes[g].Rs, qg));
-          const u64 C = h_mulmod(Lmod(i, qg), (u64)(Rbig % qg), qg);
+          const u64 qq = (u64)q[g];
+          lenter.push_back((i64)h_mulmod(Lmod(i, qq), (u64)c->primes[g].Rs, qq));
+          const u64 C = h_mulmod(Lmod(i, qq), (u64)(Rbig % qq), qq);
           lenter2.push_back(C);
-          lenter2.push_back(h_shoup(C, qg));
+          lenter2.push_back(h_shoup(C, qq));
         }
     }
   }
@@ -331,6 +388,15 @@ extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int
     return nullptr;
   }
   return c;
+}
+
+extern "C" tb200_ctx* tb200_ctx_create(int device, int logN, int num_primes, int num_special, const int64_t* q,
+                                       int scale_bits) {
+  return ctx_create_impl(device, logN, num_primes, num_special, q, scale_bits, 0, 1);
+}
+extern "C" tb200_ctx* tb200_ctx_create_sharded(int device, int logN, int num_primes, int num_special,
+                                               const int64_t* q, int scale_bits, int rank, int world) {
+  return ctx_create_impl(device, logN, num_primes, num_special, q, scale_bits, rank, world);
 }
 
 extern "C" int tb200_ctx_get_prime_consts(const tb200_ctx* c, int64_t* out) {
@@ -732,8 +798,9 @@ extern "C" int tb200_codec_rotate(tb200_ctx* c, int rows, const tb200_poly* a, c
   return 0;
 }
 
-static int moddown(tb200_ctx* c, int level, int batch, TbView cc, TbView p, TbView add, TbView out, int tail,
+static int moddown(tb200_ctx* c, int lvl_, int batch, TbView cc, TbView p, TbView add, TbView out, int tail,
                    tb200_stream st) {
+  const int level = c->lstart[lvl_];  // index of the first alive ordinary prime in the (local) prime table
   const int L = c->num_ord - level;
   LAUNCH(k_chain_backward, grid_pw(c, 1, batch, 1), dim3(256), st, c->dev(), p, (const i64*)c->d_pir_sp, c->K,
          c->num_ord, c->N);
@@ -762,7 +829,7 @@ static int moddown(tb200_ctx* c, int level, int batch, TbView cc, TbView p, TbVi
 
 extern "C" int tb200_divide_by_p(tb200_ctx* c, int level, const tb200_poly* cc, const tb200_poly* p,
                                  const tb200_poly* out, tb200_stream st) {
-  if (!c || level < 0 || level >= c->num_ord) return fail(TB200_EINVAL, "divide_by_p: bad level");
+  if (!c || level < 0 || level >= c->num_levels) return fail(TB200_EINVAL, "divide_by_p: bad level");
   CHECK_POLY(cc);
   CHECK_POLY(p);
   CHECK_POLY(out);
@@ -778,10 +845,14 @@ extern "C" int tb200_divide_by_p(tb200_ctx* c, int level, const tb200_poly* cc, 
 // ------------------------------------------------------------------------------------------------
 static int check_level(const tb200_ctx* c, int level, int batch) {
   if (!c) return fail(TB200_EINVAL, "null context");
-  if (level < 0 || level >= c->num_ord) return fail(TB200_EINVAL, "level %d outside [0, %d)", level, c->num_ord);
+  if (level < 0 || level >= c->num_levels) return fail(TB200_EINVAL, "level %d outside [0, %d)", level, c->num_levels);
   if (batch < 1) return fail(TB200_EINVAL, "batch must be >= 1");
   return 0;
 }
+#define REQUIRE_UNSHARDED()                                                                                   \
+  if (c->world > 1)                                                                                           \
+  return fail(TB200_EINVAL, "this entry point needs an unsharded context; limb-sharded contexts support the " \
+                            "op layer and tb200_ks_digits / tb200_ks_finish")
 static inline TbView shift(TbView v, long b) {
   v.p += b * v.bs;
   return v;
@@ -800,6 +871,7 @@ extern "C" int tb200_rescale(tb200_ctx* c, int level, int batch, const tb200_pol
                              const tb200_poly* out0, const tb200_poly* out1, int exact, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   if (level + 1 >= c->num_ord) return fail(TB200_EINVAL, "rescale: level %d is the last level", level);
   CHECK_POLY(in0);
   CHECK_POLY(out0);
@@ -831,61 +903,59 @@ static int make_key(const tb200_ctx* c, int level, const tb200_ksk* k, TbKskDev*
   return 0;
 }
 
-// workspace elements needed by the key switch of one ciphertext at `level`
+// workspace elements needed by the key switch of one ciphertext at `level` (state | ext | acc)
 static size_t ks_ws_elems(const tb200_ctx* c, int level) {
-  const size_t L = c->num_ord - level, E = L + c->K, ng = c->ks[level].ngroups;
-  return (L + ng * E + 2 * E) * (size_t)c->N;
+  const size_t L = c->num_ord - c->lstart[level], E = L + c->K, ng = c->ks[level].ngroups;
+  return ((size_t)c->ks[level].state_rows + ng * E + 2 * E) * (size_t)c->N;
 }
 
-// key switch of `nb` polynomials (nb <= chunk). a: coefficient canonical [L][N].
-// tail: 0 -> out0 = ks0 ; 1 -> out0 = CS1(add0 + ks0), out1 = CS1(add1 + ks1) ; 2 -> out0 = CS1(CS2(add0 + ks0)), out1 = ks1
-static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKskDev& key, TbView add0, TbView add1,
-                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st) {
-  const int N = c->N, L = c->num_ord - level, E = L + c->K;
+// key switch, part 1: mixed-radix digits of the digit groups this rank owns -> rows of the state buffer
+static int ks_digits(tb200_ctx* c, int level, int nb, TbView a, TbView state, tb200_stream st) {
+  const TbKsLevel& lv = c->ks[level];
+  if (lv.nown > 0)
+    LAUNCH(k_digits, dim3((unsigned)((c->N + 255) / 256), (unsigned)lv.nown, (unsigned)nb), dim3(256), st, c->dev(),
+           c->d_ks + level, a, state, c->N);
+  return 0;
+}
+
+// key switch, part 2: from the complete digit state to the (local) output rows.
+// tail: 0 -> out0 = ks0 ; 1 -> out = CS1(add + ks) for both ; 2 -> out0 = CS1(CS2(add0 + ks0)), out1 = ks1
+static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskDev& key, TbView add0, TbView add1,
+                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st) {
+  const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
   const TbKsLevel& lv = c->ks[level];
   const int ng = lv.ngroups;
   const TbKsLevel* dlv = c->d_ks + level;
-  i64* state = ws;
-  i64* ext = state + (size_t)nb * L * N;
+  i64* ext = ws;
   i64* acc = ext + (size_t)nb * ng * E * N;
   const TbDev d = c->dev();
-  // 1. digits
-  LAUNCH(k_digits, dim3((unsigned)((N + 255) / 256), (unsigned)ng, (unsigned)nb), dim3(256), st, d, dlv, a,
-         dense(state, L, N), level, N);
+  int rc = 0;
   if (c->fast) {
-    // 2+3. ModUp extend fused into forward pass A, then pass B (mod-q path)
+    // ModUp extend fused into forward pass A, then pass B (mod-q path)
     TbFwdAArgs fa;
     memset(&fa, 0, sizeof(fa));
-    fa.src = dense(state, L, N);
+    fa.src = state;
     fa.dst = dense(ext, E, N);
     fa.lv = dlv;
     fa.lenter2 = c->d_lenter2;
-    fa.prime0 = level;
+    fa.prime0 = p0;
     fa.ngroups = ng;
-    int rcf = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st);
-    if (rcf) return rcf;
-    if ((rcf = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, level, st))) return rcf;
-    // 4. key inner product, 128-bit accumulation over the groups
+    if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) return rc;
+    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, st))) return rc;
+    // key inner product, 128-bit accumulation over the groups
     LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),
-           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, level, N, E, nb);
-    // 5. back to coefficients, canonical
-    if ((rcf = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, st))) return rcf;
+           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb);
+    // back to coefficients, canonical
+    if ((rc = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, st))) return rc;
   } else {
-  // 2. extend every group to the L+K limbs
-  LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
-         dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, dense(state, L, N), ext, level, N, E);
-  // 3. NTT (stages only) of the nb*ng extended polynomials
-  int rc = ntt_forward(c, dense(ext, E, N), dense(ext, E, N), E, nb * ng, level, false, st);
-  if (rc) return rc;
-  // 4. inner product with the key, accumulated over groups
-  LAUNCH(k_mac, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)nb), dim3(N / 2 < 256 ? N / 2 : 256), st,
-         d, dlv, key, (const i64*)ext, acc, level, N, E);
-  // 5. back to coefficients, canonical
-  rc = ntt_inverse(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, 2, st);
-  if (rc) return rc;
+    LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
+           dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, state, ext, p0, N, E);
+    if ((rc = ntt_forward(c, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, false, st))) return rc;
+    LAUNCH(k_mac, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)nb), dim3(N / 2 < 256 ? N / 2 : 256), st,
+           d, dlv, key, (const i64*)ext, acc, p0, N, E);
+    if ((rc = ntt_inverse(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, 2, st))) return rc;
   }
-  int rc = 0;
-  // 6. ModDown (+ fused tail)
+  // ModDown (+ fused tail)
   for (int h = 0; h < 2; ++h) {
     TbView cc;
     cc.p = acc + (size_t)h * E * N;
@@ -894,9 +964,70 @@ static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKs
     TbView p = cc;
     p.p += (size_t)L * N;
     const int t = (tail == 2 && h == 1) ? 0 : tail;
-    rc = moddown(c, level, nb, cc, p, h == 0 ? add0 : add1, h == 0 ? out0 : out1, t, st);
+    if ((rc = moddown(c, level, nb, cc, p, h == 0 ? add0 : add1, h == 0 ? out0 : out1, t, st))) return rc;
+  }
+  return 0;
+}
+
+// key switch of `nb` polynomials (nb <= chunk) on an unsharded context. a: coefficient canonical [L][N].
+static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKskDev& key, TbView add0, TbView add1,
+                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st) {
+  const int S = c->ks[level].state_rows;
+  TbView state = dense(ws, S, c->N);
+  int rc = ks_digits(c, level, nb, a, state, st);
+  if (rc) return rc;
+  return ks_finish(c, level, nb, state, key, add0, add1, out0, out1, tail, ws + (size_t)nb * S * c->N, st);
+}
+
+extern "C" int tb200_ks_state_info(const tb200_ctx* c, int level, int32_t* out) {
+  if (!c || !out || level < 0 || level >= c->num_levels) return fail(TB200_EINVAL, "ks_state_info: bad arguments");
+  const TbKsLevel& lv = c->ks[level];
+  out[0] = lv.state_rows;
+  out[1] = lv.seg_rows * c->rank;
+  out[2] = lv.seg_rows;
+  out[3] = c->num_ord - c->lstart[level];
+  return 0;
+}
+extern "C" int tb200_ctx_local_primes(const tb200_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(TB200_EINVAL, "null");
+  for (int i = 0; i < c->num_ord; ++i) out[i] = c->ord_gid[i];
+  for (int kk = 0; kk < c->K; ++kk) out[c->num_ord + kk] = (int)c->qg.size() - c->K + kk;
+  return 0;
+}
+extern "C" int tb200_ks_digits(tb200_ctx* c, int level, int batch, const tb200_poly* a, const tb200_poly* state,
+                               tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (c->ks[level].nown > 0) CHECK_POLY(a);
+  CHECK_POLY(state);
+  CK(cudaSetDevice(c->device));
+  if ((rc = ks_digits(c, level, batch, view(a), view(state), st))) return rc;
+  POST();
+  return 0;
+}
+extern "C" int tb200_ks_finish(tb200_ctx* c, int level, int batch, const tb200_poly* state, const tb200_ksk* ksk,
+                               const tb200_poly* add0, const tb200_poly* add1, const tb200_poly* out0,
+                               const tb200_poly* out1, int tail, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (tail < 0 || tail > 2) return fail(TB200_EINVAL, "ks_finish: tail must be 0, 1 or 2");
+  CHECK_POLY(state);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  if (tail != 0) CHECK_POLY(add0);
+  if (tail == 1) CHECK_POLY(add1);
+  TbKskDev key;
+  if ((rc = make_key(c, level, ksk, &key))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * ch))) return rc;
+  for (int b0 = 0; b0 < batch; b0 += ch) {
+    const int nb = batch - b0 < ch ? batch - b0 : ch;
+    rc = ks_finish(c, level, nb, shift(view(state), b0), key, shift(view(add0 ? add0 : out0), b0),
+                   shift(view(add1 ? add1 : out1), b0), shift(view(out0), b0), shift(view(out1), b0), tail, c->ws, st);
     if (rc) return rc;
   }
+  POST();
   return 0;
 }
 
@@ -904,6 +1035,7 @@ extern "C" int tb200_keyswitch(tb200_ctx* c, int level, int batch, const tb200_p
                                const tb200_poly* out0, const tb200_poly* out1, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   CHECK_POLY(a);
   CHECK_POLY(out0);
   CHECK_POLY(out1);
@@ -927,6 +1059,7 @@ extern "C" int tb200_switch_key(tb200_ctx* c, int level, int batch, const tb200_
                                 tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   CHECK_POLY(c0);
   CHECK_POLY(c1);
   CHECK_POLY(out0);
@@ -951,6 +1084,7 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
                             const tb200_poly* out1, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   CHECK_POLY(c0);
   CHECK_POLY(c1);
   CHECK_POLY(out0);
@@ -1022,6 +1156,7 @@ extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const t
                                      const tb200_poly* d1, const tb200_poly* d2, int pre_rescale, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   if (pre_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "cc_mult: no level left to rescale");
   CHECK_POLY(a0);
   CHECK_POLY(a1);
@@ -1061,6 +1196,7 @@ extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200
                                  const tb200_poly* out1, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   CHECK_POLY(d0);
   CHECK_POLY(d1);
   CHECK_POLY(d2);
@@ -1099,6 +1235,7 @@ extern "C" int tb200_cc_mult_relin(tb200_ctx* c, int level, int batch, const tb2
                                    const tb200_poly* out0, const tb200_poly* out1, int pre_rescale, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   if (pre_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "cc_mult: no level left to rescale");
   CHECK_POLY(a0);
   CHECK_POLY(a1);
@@ -1135,6 +1272,7 @@ extern "C" int tb200_pc_mult(tb200_ctx* c, int level, int batch, const tb200_pol
                              tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   if (post_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "pc_mult: no level left to rescale");
   CHECK_POLY(pt);
   CHECK_POLY(c0);
@@ -1180,6 +1318,7 @@ extern "C" int tb200_cc_addsub(tb200_ctx* c, int level, int batch, int sub, cons
                                const tb200_poly* out1, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
+  REQUIRE_UNSHARDED();
   CHECK_POLY(a0);
   CHECK_POLY(a1);
   CHECK_POLY(b0);

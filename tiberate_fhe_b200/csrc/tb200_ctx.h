@@ -65,6 +65,10 @@ struct tb200_ctx {
   int device = 0, logN = 0, N = 0, P = 0, K = 0, LA = 0, LB = 0, scale_bits = 40, num_ord = 0;
   int num_levels = 0;  // levels 0..num_ord-1 (level = number of dropped scale primes)
   int chunk = 4;
+  int rank = 0, world = 1;       // RNS-limb sharding: this context holds the primes owned by `rank`
+  std::vector<int> ord_gid;      // global id of every local ordinary prime (ascending)
+  std::vector<i64> qg;           // the global prime chain
+  std::vector<int> lstart;       // per global level: local index of the first ordinary prime still alive
   std::vector<i64> q;
   std::vector<u64> k;
   std::vector<TbPrime> primes;

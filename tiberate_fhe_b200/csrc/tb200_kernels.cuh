@@ -331,40 +331,47 @@ __global__ void __launch_bounds__(256) k_automorphism(TbDev c, TbView a, TbView 
 // ---- key-switch tables -------------------------------------------------------------------------
 struct TbKsGroup {       // one digit group at one level
   int alpha;             // primes alive in the group
-  int first_row;         // row of the group's first prime inside the level tensor
+  int state_row0;        // first row of the group's digits inside the digit-state buffer
   int gid;               // global group id (index into the key-switch key)
+  int src_row0;          // owner only: row of the group's first prime inside the (local) input tensor, else -1
+  int src_prime0;        // owner only: index of that prime in the context's prime table
   int pad;
   long lenter_off;       // offset of this group's L_enter block [(alpha-1)][P] in TbKsTables.lenter
   i64 Y[TB_MAXA];        // Y[i] = (L_i^-1 mod m_{i+1}) R mod m_{i+1}
   i64 Lsc[TB_MAXA][TB_MAXA];  // Lsc[i][j] = L_i R mod m_j for j >= i+2
 };
 struct TbKsLevel {
-  int ngroups, L, pad0, pad1;
+  int ngroups, L;        // alive digit groups (all ranks'), local ordinary rows at this level
+  int nown;              // groups whose digits this rank computes
+  int state_rows;        // rows of the digit-state buffer (= world * seg_rows; owner-major layout)
+  int seg_rows;          // rows of one rank's segment
+  int pad;
+  int own[TB_MAXG];      // indices into g[] of the owned groups
   TbKsGroup g[TB_MAXG];
 };
 
 // ModUp digits (pre_extend, ckks_engine.py:889-921): one thread per (coefficient, group).
 // a: [L][N] canonical coefficient domain; state: [L][N] (digit rows, same row numbering).
-__global__ void __launch_bounds__(256) k_digits(TbDev c, const TbKsLevel* lv, TbView a, TbView st, int level, int N) {
-  const TbKsGroup& G = lv->g[blockIdx.y];
+__global__ void __launch_bounds__(256) k_digits(TbDev c, const TbKsLevel* lv, TbView a, TbView st, int N) {
+  const TbKsGroup& G = lv->g[lv->own[blockIdx.y]];
   const int bt = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
   const int alpha = G.alpha;
   i64 s[TB_MAXA];
-  const i64 a0 = a.row(bt, G.first_row)[j];
+  const i64 a0 = a.row(bt, G.src_row0)[j];
 #pragma unroll
   for (int i = 0; i < TB_MAXA; ++i) s[i] = a0;
 #pragma unroll
   for (int i = 0; i < TB_MAXA - 1; ++i) {
     if (i + 1 < alpha) {
-      const TbPrime& P1 = c.pr[level + G.first_row + i + 1];
-      const i64 Y = tb_mm_ss(a.row(bt, G.first_row + i + 1)[j] - s[i + 1], G.Y[i], P1.q4, P1.k);
+      const TbPrime& P1 = c.pr[G.src_prime0 + i + 1];
+      const i64 Y = tb_mm_ss(a.row(bt, G.src_row0 + i + 1)[j] - s[i + 1], G.Y[i], P1.q4, P1.k);
       s[i + 1] = Y;
 #pragma unroll
       for (int jj = i + 2; jj < TB_MAXA; ++jj) {
         if (jj < alpha) {
-          const TbPrime& Pj = c.pr[level + G.first_row + jj];
+          const TbPrime& Pj = c.pr[G.src_prime0 + jj];
           s[jj] += tb_mm_ss(Y, G.Lsc[i][jj], Pj.q4, Pj.k);
         }
       }
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(256) k_digits(TbDev c, const TbKsLevel* lv, Tb
   }
 #pragma unroll
   for (int i = 0; i < TB_MAXA; ++i)
-    if (i < alpha) st.row(bt, G.first_row + i)[j] = s[i];
+    if (i < alpha) st.row(bt, G.state_row0 + i)[j] = s[i];
 }
 
 // ModUp extend for every group of the level (he_fused_cuda.cu:298-311):
@@ -386,11 +393,11 @@ __global__ void __launch_bounds__(256) k_extend_all(TbDev c, const TbKsLevel* lv
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (j >= N) return;
   const i64* le = lenter + G.lenter_off + (level + t);
-  longlong2 d = *reinterpret_cast<const longlong2*>(st.row(bt, G.first_row) + j);
+  longlong2 d = *reinterpret_cast<const longlong2*>(st.row(bt, G.state_row0) + j);
   i64 x0 = tb_mm_ss(d.x, P.Rs, P.q4, P.k);
   i64 x1 = tb_mm_ss(d.y, P.Rs, P.q4, P.k);
   for (int kk = 1; kk < G.alpha; ++kk) {
-    d = *reinterpret_cast<const longlong2*>(st.row(bt, G.first_row + kk) + j);
+    d = *reinterpret_cast<const longlong2*>(st.row(bt, G.state_row0 + kk) + j);
     const i64 s = le[(long)(kk - 1) * c.P];
     x0 = tb_add(x0, tb_mm_ss(d.x, s, P.q4, P.k), P.q2);
     x1 = tb_add(x1, tb_mm_ss(d.y, s, P.q4, P.k), P.q2);

@@ -57,7 +57,7 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
     Cs[k] = le[1];
     le += 2 * nP;
   }
-  const i64* base = a.src.row(bt, G.first_row) + c0;
+  const i64* base = a.src.row(bt, G.state_row0) + c0;
 #pragma unroll
   for (int h = 0; h < 16; h += 4) {
     i64 d[4][ALPHA];

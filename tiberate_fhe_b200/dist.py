@@ -51,3 +51,61 @@ def gather_batch(local, total: int, group=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# RNS-limb sharding for the largest rings (BASELINE.json configs[3])
+# ------------------------------------------------------------------------------------------------
+class LimbShardedKeySwitch:
+    """Key switch of a polynomial whose limbs are dealt to ranks by digit group
+    (tiberate/context/rns_partition.py:34-52; the reference moves the digit states with per-device
+    `tensor.to(device)` copies, ckks_engine.py:1248-1265).
+
+    Per call: each rank computes the ModUp digits of the groups it owns (tb200_ks_digits), ONE
+    all-gather completes the digit-state buffer on every rank (its layout is owner-major with equal
+    segments, so the gather is in place and copy-free), then each rank extends / transforms /
+    multiplies / ModDowns its own limbs (tb200_ks_finish).  The special limbs are replicated, as in
+    the reference, so ModDown needs no second exchange.
+    """
+
+    def __init__(self, ctx, group=None):
+        import torch.distributed as dist
+
+        self.ctx, self.group = ctx, group
+        self.world = dist.get_world_size(group)
+        if ctx.world != self.world or ctx.rank != dist.get_rank(group):
+            raise ValueError("context rank/world must match the process group")
+        self._state = {}
+
+    def _state_buffer(self, level, like):
+        import torch
+
+        S, row0, seg, _ = self.ctx.ks_state_info(level)
+        key = (level, like.device)
+        st = self._state.get(key)
+        if st is None:
+            st = torch.zeros(S, self.ctx.N, dtype=torch.int64, device=like.device)
+            self._state[key] = st
+        return st, row0, seg
+
+    def __call__(self, level: int, a_local, ksk_local, out0, out1, add0=None, add1=None, tail: int = 0):
+        """a_local / out*: this rank's rows [L_local, N] (coefficient domain, canonical);
+        ksk_local: KeySwitchKeyView over the LOCAL key rows ([P_local, N] per digit group)."""
+        import torch.distributed as dist
+
+        state, row0, seg = self._state_buffer(level, out0)
+        self.ctx.ks_digits(level, a_local, state)
+        if self.world > 1:
+            views = [state[r * seg:(r + 1) * seg] for r in range(self.world)]
+            dist.all_gather(views, state[row0:row0 + seg], group=self.group)
+        self.ctx.ks_finish(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
+        return out0, out1
+
+
+def shard_rows(t, ctx, level: int, with_special: bool = False):
+    """Rows of a full [L(+K), N] level-`level` tensor that live on ctx's rank (a copy, contiguous)."""
+    rows = [g - level for g in ctx.local_rows(level)]
+    if with_special:
+        n_ord = ctx.P_global - ctx.K - level
+        rows += list(range(n_ord, n_ord + ctx.K))
+    return t[rows].contiguous()
