@@ -92,7 +92,7 @@ def _sharded_ks_worker(rank, world, port, seed):
         key = KeySwitchKeyView([None if p is None else (torch.from_numpy(np.ascontiguousarray(p[0][ids])),
                                                         torch.from_numpy(np.ascontiguousarray(p[1][ids]))) for p in evk],
                                octx.N)
-        for level in (0, 2):
+        for level in (0, 2, 4):  # at level 4 rank 1 owns no ordinary limb any more
             a = eng.uniform(rng, octx.level_primes(level, False))
             want0, want1 = eng.create_switcher(a, evk, level)
             a_loc = shard_rows(torch.from_numpy(a), ctx, level)

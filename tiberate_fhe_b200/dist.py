@@ -94,11 +94,14 @@ class LimbShardedKeySwitch:
         import torch.distributed as dist
 
         state, row0, seg = self._state_buffer(level, out0)
-        self.ctx.ks_digits(level, a_local, state)
-        if self.world > 1:
+        has_rows = out0.shape[-2] > 0  # deep levels can leave a rank without ordinary limbs
+        if has_rows:
+            self.ctx.ks_digits(level, a_local, state)
+        if self.world > 1:  # every rank takes part, also those that own nothing at this level
             views = [state[r * seg:(r + 1) * seg] for r in range(self.world)]
             dist.all_gather(views, state[row0:row0 + seg], group=self.group)
-        self.ctx.ks_finish(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
+        if has_rows:
+            self.ctx.ks_finish(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
         return out0, out1
 
 
