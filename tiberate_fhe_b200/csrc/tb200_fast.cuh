@@ -8,7 +8,7 @@
 // reference's lazy Montgomery representatives.  This path uses Harvey butterflies with Shoup
 // twiddles (w, w' = floor(w 2^64 / q)):  V = O*w - umulhi(O, w')*q  in [0, 2q) for ANY 64-bit O,
 //   * "small" primes (q < 2^42, the 40-bit scale primes = 34 of 39 limbs at logN16): no conditional
-//     subtraction at all -- forward values grow by 2q per stage (< 36q < 2^47 after 17 stages),
+//     subtraction at all -- forward values grow by 4q per stage (< 72q < 2^49 after 17 stages),
 //     inverse values double per stage (< 2^(2+17) q < 2^61);
 //   * other primes (the 60-bit base / special primes): one conditional subtraction per butterfly,
 //     values in [0, 4q) (forward) / [0, 2q) (inverse).
@@ -39,6 +39,16 @@ __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws, u64 q) {
   return x * w - h * q;  // in [0, 2q)
 }
 
+// Shoup product with an approximate quotient (the low x low partial product and the carries of the
+// cross terms are dropped): the quotient is short by at most 2, so the result lies in [0, 4q).
+// Three 32-bit multiplies instead of the four (plus carry chain) of an exact umulhi.
+__device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
+  const unsigned xh = (unsigned)(x >> 32), xl = (unsigned)x;
+  const unsigned wh = (unsigned)(ws >> 32), wl = (unsigned)ws;
+  const u64 h = (u64)xh * wh + __umulhi(xh, wl) + __umulhi(xl, wh);
+  return x * w - h * q;
+}
+
 __device__ __forceinline__ TbTw2 load_tw2(const TbTw2* p) {
 #ifndef TB200_HOST_EMU
   const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
@@ -51,7 +61,7 @@ __device__ __forceinline__ TbTw2 load_tw2(const TbTw2* p) {
 #endif
 }
 
-// q < 2^42: no reductions.  Forward: values < B0 + 2q * stages.  Inverse: inputs < 4q, the bound
+// q < 2^42: no reductions.  Forward: values < B0 + 4q * stages (lazy Shoup quotient).  Inverse: inputs < 4q, the bound
 // doubles per stage; `off` = q << (2 + stage) keeps U - V non-negative and is a multiple of q.
 struct FastSmallPol {
   u64 q, q2;
@@ -59,15 +69,15 @@ struct FastSmallPol {
   typedef TbTw2 TW;
   static __device__ __forceinline__ TW load(const TW* t) { return load_tw2(t); }
   __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
-    const u64 u = (u64)U, v = shoup((u64)O, S.w, S.ws, q);
+    const u64 u = (u64)U, v = shoup_lazy((u64)O, S.w, S.ws, q);  // v < 4q
     U = (i64)(u + v);
-    O = (i64)(u + q2 - v);
+    O = (i64)(u + 2 * q2 - v);
   }
   __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int mlog) const {
     const u64 u = (u64)U, v = (u64)V;
     const u64 off = q << (2 + (logN - 1 - mlog));
     U = (i64)(u + v);
-    V = (i64)shoup(u + off - v, S.w, S.ws, q);
+    V = (i64)shoup_lazy(u + off - v, S.w, S.ws, q);  // < 4q <= bound of the next stage
   }
 };
 

@@ -26,16 +26,18 @@ struct TbFwdAArgs {
 
 template <int PRO>
 __device__ __forceinline__ i64 fast_prologue(const TbFwdAArgs& a, const TbFastPrime& P, int bt, int gi, int limb,
-                                             long col_off, int g, int nP) {
+                                             unsigned col_off, int g, int nP) {
   if constexpr (PRO == TB_FPRO_ENTER) {
     const i64 v = a.src.row(bt, limb)[col_off];
-    return (i64)tb::shoup((u64)(v + (i64)P.q), P.Rm, P.Rm_s, P.q);
+    return (i64)(P.small ? tb::shoup_lazy((u64)(v + (i64)P.q), P.Rm, P.Rm_s, P.q)
+                         : tb::shoup((u64)(v + (i64)P.q), P.Rm, P.Rm_s, P.q));
   } else if constexpr (PRO == TB_FPRO_RESCALE_ENTER) {
     const i64 v = a.src.row(bt, limb + 1)[col_off];
     const i64 r = a.src.row(bt, 0)[col_off];
     const u64* c = a.resc + 3 * limb;
-    u64 x = tb::shoup((u64)(v - r + (i64)c[2]), c[0], c[1], P.q);
-    x += (r > a.round_at) ? P.Rm : 0ull;
+    const u64 t = (u64)(v - r + (i64)c[2]);
+    u64 x = P.small ? tb::shoup_lazy(t, c[0], c[1], P.q) : tb::shoup(t, c[0], c[1], P.q);
+    x += (r > a.round_at) ? P.Rm : 0ull;  // small primes: < 5q, others: < 3q
     return (i64)x;
   } else {
     return 0;  // EXTEND is handled by extend_prologue<ALPHA> (all 16 residues of a thread at once)
@@ -46,7 +48,7 @@ __device__ __forceinline__ i64 fast_prologue(const TbFwdAArgs& a, const TbFastPr
 template <int ALPHA>
 __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& a, const TbFastPrime& P,
                                                 const TbKsGroup& G, int bt, int g, int nP, int tr, int f0, int LB,
-                                                long c0) {
+                                                unsigned c0) {
   u64 C[ALPHA], Cs[ALPHA];
   C[0] = P.Rm;
   Cs[0] = P.Rm_s;
@@ -58,20 +60,28 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
     le += 2 * nP;
   }
   const i64* base = a.src.row(bt, G.state_row0) + c0;
+  const unsigned rs = (unsigned)a.src.rs;  // state rows are dense: row stride N < 2^31 / alpha
 #pragma unroll
   for (int h = 0; h < 16; h += 4) {
     i64 d[4][ALPHA];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int k = 0; k < ALPHA; ++k) d[i][k] = base[(long)k * a.src.rs + ((long)tb::tile_x(tr, h + i, f0) << LB)];
+      for (int k = 0; k < ALPHA; ++k) d[i][k] = base[(unsigned)k * rs + ((unsigned)tb::tile_x(tr, h + i, f0) << LB)];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      u64 v = tb::shoup((u64)(d[i][0] + (i64)P.off), C[0], Cs[0], P.q);
+      u64 v;
+      if (P.small) {  // lazy quotients: every term < 4q, sum < 4 ALPHA q
+        v = tb::shoup_lazy((u64)(d[i][0] + (i64)P.off), C[0], Cs[0], P.q);
 #pragma unroll
-      for (int k = 1; k < ALPHA; ++k) {
-        v += tb::shoup((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
-        if (!P.small) v = (v >= P.q2) ? v - P.q2 : v;
+        for (int k = 1; k < ALPHA; ++k) v += tb::shoup_lazy((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
+      } else {
+        v = tb::shoup((u64)(d[i][0] + (i64)P.off), C[0], Cs[0], P.q);
+#pragma unroll
+        for (int k = 1; k < ALPHA; ++k) {
+          v += tb::shoup((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
+          v = (v >= P.q2) ? v - P.q2 : v;
+        }
       }
       x[h + i] = (i64)v;
     }
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a
     gi = blockIdx.z % a.ngroups;
     bt = blockIdx.z / a.ngroups;
   }
-  const long c0 = (long)blockIdx.x * W + col;
+  const unsigned c0 = blockIdx.x * W + col;
   i64* d = a.dst.row(blockIdx.z, limb) + c0;
   constexpr int f0 = tb::fwd_field<LA>(0);
   i64 x[16];
@@ -108,7 +118,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((long)tb::tile_x(tr, i, f0) << c.LB) + c0, g, c.P);
+      x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((unsigned)tb::tile_x(tr, i, f0) << c.LB) + c0, g, c.P);
   }
   auto slot = [&](int lx) { return tb::pad16((lx << a.LW) | col); };
   const TbTw2* tw = c.tw + ((long)g << c.logN);
@@ -117,75 +127,85 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a
   else
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = x[i];
+  for (int i = 0; i < 16; ++i) d[(unsigned)tb::tile_x(tr, i, 0) << c.LB] = x[i];
 }
 
-// forward pass B; outputs: small primes < 38q, other primes reduced to [0, 2q).
+// forward pass B; outputs: small primes < 72q, other primes reduced to [0, 2q).
+// A CTA owns one (limb, 4096-residue tile) and can walk over `bper` consecutive batch entries (the
+// launcher uses bper = 1: see launch_fast_B for the measurement).
 template <int LB>
-__global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst, int prime0, int batch,
+                                                       int bper) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
   const TbFastPrime P = c.fp[g];
   const long e0 = (long)blockIdx.x * nt * 16;
-  const i64* s = src.row(blockIdx.z, limb) + e0;
-  i64* d = dst.row(blockIdx.z, limb) + e0;
   const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
   const int tile = (int)(e0 >> LB) + blk;
   auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
   constexpr int f0 = tb::fwd_field<LB>(0);
-  i64 x[16];
-  // round-0 layout: 16 consecutive threads read 16 consecutive residues (one 128-byte line)
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
   const TbTw2* tw = c.tw + ((long)g << c.logN);
-  if (P.small) {
-    tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-  } else {
-    tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+  {
+    const int z = blockIdx.z;  // one batch entry per CTA (bper == 1, see launch_fast_B)
+    const i64* s = src.row(z, limb) + e0;
+    i64* d = dst.row(z, limb) + e0;
+    i64 x[16];
+    // round-0 layout: 16 consecutive threads read 16 consecutive residues (one 128-byte line)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
-  }
-  // final layout (field 0): a thread owns 16 consecutive residues -> eight 128-bit stores
-  longlong2* dv = reinterpret_cast<longlong2*>(d + ((blk << LB) | (lt << 4)));
+    for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
+    if (P.small) {
+      tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+    } else {
+      tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    longlong2 v;
-    v.x = x[2 * i];
-    v.y = x[2 * i + 1];
-    dv[i] = v;
+      for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
+    }
+    // final layout (field 0): a thread owns 16 consecutive residues -> eight 128-bit stores
+    longlong2* dv = reinterpret_cast<longlong2*>(d + ((blk << LB) | (lt << 4)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      longlong2 v;
+      v.x = x[2 * i];
+      v.y = x[2 * i + 1];
+      dv[i] = v;
+    }
   }
 }
 
 // inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
 template <int LB>
-__global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst, int prime0, int batch,
+                                                       int bper) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
   const TbFastPrime P = c.fp[g];
   const long e0 = (long)blockIdx.x * nt * 16;
-  const i64* s = src.row(blockIdx.z, limb) + e0;
-  i64* d = dst.row(blockIdx.z, limb) + e0;
   const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
   const int tile = (int)(e0 >> LB) + blk;
   auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
   constexpr int f0 = tb::fwd_field<LB>(0);
-  i64 x[16];
-  const longlong2* sv = reinterpret_cast<const longlong2*>(s + ((blk << LB) | (lt << 4)));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const longlong2 v = sv[i];
-    x[2 * i] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
-    x[2 * i + 1] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
-  }
   const TbTw2* tw = c.itw + ((long)g << c.logN);
-  if (P.small)
-    tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-  else
-    tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+  {
+    const int z = blockIdx.z;  // one batch entry per CTA (bper == 1, see launch_fast_B)
+    const i64* s = src.row(z, limb) + e0;
+    i64* d = dst.row(z, limb) + e0;
+    i64 x[16];
+    const longlong2* sv = reinterpret_cast<const longlong2*>(s + ((blk << LB) | (lt << 4)));
 #pragma unroll
-  for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = x[i];
+    for (int i = 0; i < 8; ++i) {
+      const longlong2 v = sv[i];  // L1-cached: neighbouring 16-byte loads share 32-byte sectors
+      x[2 * i] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
+      x[2 * i + 1] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
+    }
+    if (P.small)
+      tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+    else
+      tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = x[i];
+  }
 }
 
 // inverse pass A' + exit: y = CS1(x * N^-1 R^-1)  == intt_radix2_exit_reduce of the reference (canonical).
@@ -201,7 +221,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
   constexpr int f0 = tb::fwd_field<LA>(0);
   i64 x[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = s[(long)tb::tile_x(tr, i, 0) << c.LB];
+  for (int i = 0; i < 16; ++i) x[i] = s[(unsigned)tb::tile_x(tr, i, 0) << c.LB];
   auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
   const TbTw2* tw = c.itw + ((long)g << c.logN);
   if (P.small)
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const u64 y = tb::shoup((u64)x[i], P.ex, P.ex_s, P.q);
-    d[(long)tb::tile_x(tr, i, f0) << c.LB] = (i64)(y >= P.q ? y - P.q : y);
+    d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = (i64)(y >= P.q ? y - P.q : y);
   }
 }
 

@@ -15,6 +15,11 @@
 #include <cuda_runtime.h>
 #define TB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define TB_KERNEL_SHARED __shared__
+// streaming (L2-only) accesses for data that is touched once per kernel
+static __device__ __forceinline__ long tb_ldcg(const long* p) { return __ldcg(p); }
+static __device__ __forceinline__ longlong2 tb_ldcg2(const longlong2* p) { return __ldcg(p); }
+static __device__ __forceinline__ void tb_stcg(long* p, long v) { __stcg(p, v); }
+static __device__ __forceinline__ void tb_stcg2(longlong2* p, longlong2 v) { __stcg(p, v); }
 #else
 // ------------------------------------------------------------------ host emulation (tests only)
 #include <cstdlib>
@@ -48,12 +53,21 @@ static inline T __ldg(const T* p) {
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
   return (unsigned long long)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) {
+  return (unsigned)(((unsigned long long)a * b) >> 32);
+}
 static inline long long __mul64hi(long long a, long long b) {
   return (long long)(((__int128)a * (__int128)b) >> 64);
 }
 struct alignas(16) longlong2 {
   long long x, y;
 };
+static inline long tb_ldcg(const long* p) { return *p; }
+static inline longlong2 tb_ldcg2(const longlong2* p) { return *p; }
+static inline void tb_stcg(long* p, long v) { *p = v; }
+static inline void tb_stcg2(longlong2* p, longlong2 v) { *p = v; }
+#include <algorithm>
+using std::min;
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0
