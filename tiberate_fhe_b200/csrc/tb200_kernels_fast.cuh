@@ -155,20 +155,27 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
     if (P.small) {
-      tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
     } else {
-      tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
     }
-    // final layout (field 0): a thread owns 16 consecutive residues -> eight 128-bit stores
-    longlong2* dv = reinterpret_cast<longlong2*>(d + ((blk << LB) | (lt << 4)));
+    // final layout (field 0): a thread owns 16 consecutive residues.  Storing them directly would make
+    // every warp instruction touch 32 different 128-byte lines (ncu: the L1TEX data pipe was 79 % busy),
+    // so transpose through shared memory and store 512 contiguous bytes per warp instruction.
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
+    __syncthreads();
+    longlong2* dv = reinterpret_cast<longlong2*>(d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      const int e = 2 * (i * nt + tid);
       longlong2 v;
-      v.x = x[2 * i];
-      v.y = x[2 * i + 1];
-      dv[i] = v;
+      v.x = sm[tb::pad16(e)];
+      v.y = sm[tb::pad16(e + 1)];
+      dv[i * nt + tid] = v;
     }
   }
 }
@@ -192,17 +199,23 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, 
     const i64* s = src.row(z, limb) + e0;
     i64* d = dst.row(z, limb) + e0;
     i64 x[16];
-    const longlong2* sv = reinterpret_cast<const longlong2*>(s + ((blk << LB) | (lt << 4)));
+    // coalesced 128-bit loads (512 contiguous bytes per warp instruction), transposed through shared
+    // memory into the field-0 layout (16 consecutive residues per thread)
+    const longlong2* sv = reinterpret_cast<const longlong2*>(s);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const longlong2 v = sv[i];  // L1-cached: neighbouring 16-byte loads share 32-byte sectors
-      x[2 * i] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
-      x[2 * i + 1] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
+      const longlong2 v = sv[i * nt + tid];
+      const int e = 2 * (i * nt + tid);
+      sm[tb::pad16(e)] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
+      sm[tb::pad16(e + 1)] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
     if (P.small)
-      tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
     else
-      tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
 #pragma unroll
     for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = x[i];
   }

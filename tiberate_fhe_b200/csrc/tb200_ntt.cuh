@@ -68,21 +68,28 @@ __host__ __device__ constexpr int num_rounds() {
 
 // One forward round: stages with local distance bits top .. top-ns+1 (descending).
 // mlog(d) = log2(number of groups) of the stage with local distance bit d.
-template <int LT, int R, class POL>
+// PERM (only meaningful for the field-0 round, where every thread owns (8 >> b) CONSECUTIVE twiddles of
+// stage b): the table stores those stages "transposed" inside each tile -- entry (t, g) at g * T + t
+// with T = 2^(LT-4) threads per tile -- so that for a fixed g the lanes of a warp read consecutive
+// 16-byte records (4 L1 wavefronts per warp instruction instead of 32).
+template <int LT, int R, class POL, bool PERM = false>
 __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlog_of_d0,
                                           const typename POL::TW* __restrict__ tw, const POL& p) {
   constexpr int f = fwd_field<LT>(R);
   constexpr int top = LT - 1 - 4 * R;
   constexpr int ns = (LT - 4 * R) > 4 ? 4 : (LT - 4 * R);
+  constexpr int T = LT > 4 ? (1 << (LT - 4)) : 1;
 #pragma unroll
   for (int s = 0; s < ns; ++s) {
     const int d = top - s;   // local distance bit
     const int b = d - f;     // register bit
     const int mlog = mlog_of_d0 - d;  // groups = 2^mlog
-    const int base = (1 << mlog) + (tile << (LT - 1 - d)) + ((t >> f) << (3 - b));
+    const bool perm = PERM && f == 0;
+    const int base = (1 << mlog) + (tile << (LT - 1 - d)) + (perm ? t : ((t >> f) << (3 - b)));
+    const int gs = perm ? T : 1;
 #pragma unroll
     for (int g = 0; g < (8 >> b); ++g) {       // distinct twiddles: register bits above b
-      const typename POL::TW S4 = POL::load(tw + base + g);
+      const typename POL::TW S4 = POL::load(tw + base + g * gs);
 #pragma unroll
       for (int l = 0; l < (1 << b); ++l) {     // register bits below b
         const int i = (g << (b + 1)) | l;
@@ -93,21 +100,24 @@ __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlo
 }
 
 // One inverse round: the same field as forward round R, stages ascending in distance.
-template <int LT, int R, class POL>
+template <int LT, int R, class POL, bool PERM = false>
 __device__ __forceinline__ void inv_round(i64 (&x)[16], int t, int tile, int mlog_of_d0,
                                           const typename POL::TW* __restrict__ tw, const POL& p) {
   constexpr int f = fwd_field<LT>(R);
   constexpr int top = LT - 1 - 4 * R;
   constexpr int ns = (LT - 4 * R) > 4 ? 4 : (LT - 4 * R);
+  constexpr int T = LT > 4 ? (1 << (LT - 4)) : 1;
 #pragma unroll
   for (int s = ns - 1; s >= 0; --s) {
     const int d = top - s;
     const int b = d - f;
     const int mlog = mlog_of_d0 - d;
-    const int base = (1 << mlog) + (tile << (LT - 1 - d)) + ((t >> f) << (3 - b));
+    const bool perm = PERM && f == 0;
+    const int base = (1 << mlog) + (tile << (LT - 1 - d)) + (perm ? t : ((t >> f) << (3 - b)));
+    const int gs = perm ? T : 1;
 #pragma unroll
     for (int g = 0; g < (8 >> b); ++g) {
-      const typename POL::TW S4 = POL::load(tw + base + g);
+      const typename POL::TW S4 = POL::load(tw + base + g * gs);
 #pragma unroll
       for (int l = 0; l < (1 << b); ++l) {
         const int i = (g << (b + 1)) | l;
@@ -131,33 +141,33 @@ __device__ __forceinline__ void exchange(i64 (&x)[16], i64* sm, int t, int fw, i
 
 // Full forward tile: rounds 0..NR-1.  On entry x is laid out with field fwd_field<LT>(0);
 // on exit with field fwd_field<LT>(NR-1) (== 0 unless LT == 4k where it is also 0).
-template <int LT, class POL, class SlotFn>
+template <int LT, bool PERM = false, class POL, class SlotFn>
 __device__ __forceinline__ void tile_fwd(i64 (&x)[16], i64* sm, int t, int tile, int mlog_of_d0,
                                          const typename POL::TW* __restrict__ tw, const POL& p, SlotFn slot) {
-  fwd_round<LT, 0>(x, t, tile, mlog_of_d0, tw, p);
+  fwd_round<LT, 0, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
   if constexpr (num_rounds<LT>() > 1) {
     exchange(x, sm, t, fwd_field<LT>(0), fwd_field<LT>(1), slot);
-    fwd_round<LT, 1>(x, t, tile, mlog_of_d0, tw, p);
+    fwd_round<LT, 1, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
   }
   if constexpr (num_rounds<LT>() > 2) {
     exchange(x, sm, t, fwd_field<LT>(1), fwd_field<LT>(2), slot);
-    fwd_round<LT, 2>(x, t, tile, mlog_of_d0, tw, p);
+    fwd_round<LT, 2, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
   }
 }
 
 // Full inverse tile: rounds NR-1..0.  Entry layout: field fwd_field<LT>(NR-1); exit: fwd_field<LT>(0).
-template <int LT, class POL, class SlotFn>
+template <int LT, bool PERM = false, class POL, class SlotFn>
 __device__ __forceinline__ void tile_inv(i64 (&x)[16], i64* sm, int t, int tile, int mlog_of_d0,
                                          const typename POL::TW* __restrict__ tw, const POL& p, SlotFn slot) {
   if constexpr (num_rounds<LT>() > 2) {
-    inv_round<LT, 2>(x, t, tile, mlog_of_d0, tw, p);
+    inv_round<LT, 2, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
     exchange(x, sm, t, fwd_field<LT>(2), fwd_field<LT>(1), slot);
   }
   if constexpr (num_rounds<LT>() > 1) {
-    inv_round<LT, 1>(x, t, tile, mlog_of_d0, tw, p);
+    inv_round<LT, 1, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
     exchange(x, sm, t, fwd_field<LT>(1), fwd_field<LT>(0), slot);
   }
-  inv_round<LT, 0>(x, t, tile, mlog_of_d0, tw, p);
+  inv_round<LT, 0, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
 }
 
 }  // namespace tb
