@@ -253,14 +253,20 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
     {
       const int LBv = c->LB, NRb = (LBv + 3) / 4, ns_last = LBv - 4 * (NRb - 1), T = 1 << (LBv - 4);
       std::vector<TbTw2> tmp;
+      std::vector<u64> tmp4;
       for (int dir = 0; dir < 2; ++dir) {
         std::vector<TbTw2>& t2 = dir == 0 ? tw2 : itw2;
+        std::vector<u64>& t4 = dir == 0 ? psi4 : ipsi4;  // the exact-path device tables use the same layout
         for (int d = 0; d < ns_last && d < 3; ++d) {
           const int m = 1 << (logN - 1 - d), per_tile = 1 << (LBv - 1 - d), G = 8 >> d;
           tmp.assign(t2.begin() + (size_t)g * N + m, t2.begin() + (size_t)g * N + 2 * m);
+          tmp4.assign(t4.begin() + (size_t)g * N + m, t4.begin() + (size_t)g * N + 2 * m);
           for (int tile0 = 0; tile0 < m; tile0 += per_tile)
             for (int t = 0; t < T; ++t)
-              for (int gg = 0; gg < G; ++gg) t2[(size_t)g * N + m + tile0 + gg * T + t] = tmp[tile0 + t * G + gg];
+              for (int gg = 0; gg < G; ++gg) {
+                t2[(size_t)g * N + m + tile0 + gg * T + t] = tmp[tile0 + t * G + gg];
+                t4[(size_t)g * N + m + tile0 + gg * T + t] = tmp4[tile0 + t * G + gg];
+              }
         }
       }
     }

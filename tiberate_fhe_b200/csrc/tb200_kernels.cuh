@@ -19,7 +19,8 @@
 
 struct TbDev {
   const TbPrime* pr;   // [P]
-  const u64* psi4;     // [P][N] forward twiddles, lazy Montgomery form, pre-shifted by 2
+  const u64* psi4;     // [P][N] forward twiddles, lazy Montgomery form, pre-shifted by 2 (the last-round
+                       // stages of pass B stored transposed per tile, see tb::fwd_round<PERM>)
   const u64* ipsi4;    // [P][N] inverse twiddles
   int logN, LA, LB, P;
 };
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd_B(TbDev c, TbView src, TbView d
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
-  tb::tile_fwd<LB>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
+  tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) k_ntt_inv_B(TbDev c, TbView src, TbView d
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
-  tb::tile_inv<LB>(x, sm, lt, tile, c.logN - 1, c.ipsi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
+  tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, c.ipsi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, f0))] = x[i];
