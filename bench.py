@@ -257,21 +257,25 @@ def run_ours(args):
     kernel_us_per_op = {k: round(1e3 * v[1] / (B * psteps), 2) for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])}
     top = max(kern, key=lambda k_: kern[k_][1]) if kern else None
     peak, peak_src = measured_peaks()
-    # limbs transformed per HMult by each NTT pass kernel (DESIGN.md "Kernels"): forward passes see
-    # 4 L (inputs) + ngroups (L+K) (ModUp) limbs, inverse passes 3 L + 2 (L+K); 16 B per residue.
+    # algorithmic limb passes (LP = N * 8 bytes) moved per HMult by each transform kernel:
+    #   forward pass A: the 4 input polys (read L+1 limbs incl. the dropped one, write L) + ModUp (read the
+    #   L digit rows once, write ngroups * (L+K) extended limbs); forward pass B: read + write of the
+    #   4 L + ngroups (L+K) limbs; inverse passes: read + write of the 3 L + 2 (L+K) limbs.
     E = L + K
-    limbs = {"k_ntt_fwd_A": 4 * L + ng * E, "k_ntt_fwd_B": 4 * L + ng * E, "k_ntt_inv_A": 3 * L + 2 * E,
-             "k_ntt_inv_B": 3 * L + 2 * E, "k_fast_fwd_A": 4 * L + ng * E, "k_fast_fwd_B": 4 * L + ng * E,
-             "k_fast_inv_A": 3 * L + 2 * E, "k_fast_inv_B": 3 * L + 2 * E}
+    fwd_limbs, inv_limbs = 4 * L + ng * E, 3 * L + 2 * E
+    limbs = {"k_ntt_fwd_A": 2 * fwd_limbs, "k_ntt_fwd_B": 2 * fwd_limbs, "k_ntt_inv_A": 2 * inv_limbs,
+             "k_ntt_inv_B": 2 * inv_limbs, "k_fast_fwd_A": 4 * (2 * L + 1) + L + ng * E,
+             "k_fast_fwd_B": 2 * fwd_limbs, "k_fast_inv_A": 2 * inv_limbs, "k_fast_inv_B": 2 * inv_limbs}
     roof = None
     if top in limbs:
         nl, tms = kern[top]
-        bytes_per_launch = B * limbs[top] * N * 16.0 * psteps / nl
+        bytes_per_launch = B * limbs[top] * N * 8.0 * psteps / nl
         ach = bytes_per_launch / (tms / nl / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": tms / nl, "launches_per_step": nl // psteps,
-                "note": "read+write of every residue once (16 B) per pass; kernel is INT-pipe bound, see DESIGN.md"}
+                "note": "algorithmic limb passes of this kernel class per HMult x N x 8 B (DESIGN.md 4); the kernel is "
+                        "bound by the integer pipes (ncu: math_pipe_throttle), not by HBM"}
     elif top is not None:
         nl, tms = kern[top]
         roof = {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
