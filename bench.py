@@ -167,6 +167,8 @@ def run_ours(args):
     q, K = preset()
     ctx = Tb200Context(LOGN, q, K, device=local)
     ctx.set_chunk(args.chunk)
+    if args.f64_share is not None:
+        ctx.set_f64_share(args.f64_share)
     N, P, no = ctx.N, ctx.P, ctx.num_ordinary
     L = no - 1
     B = args.batch
@@ -404,6 +406,8 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64)
     ap.add_argument("--e2e-sub", type=int, default=8, help="sub-batch of the end-to-end pipeline")
     ap.add_argument("--no-reference-ext", action="store_true")
+    ap.add_argument("--f64-share", type=int, default=None,
+                    help="eighths of the 40-bit-prime limbs transformed on the FP64 pipe (default: library default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the secondary rotate / NTT figures and the reference ext")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -80,6 +80,10 @@ int tb200_ctx_set_chunk(tb200_ctx*, int chunk);
  * op-layer kernels.  Outputs are bit-identical either way (every internal chain ends in a
  * canonicalising step); the switch exists for A/B tests and measurements. */
 int tb200_ctx_set_fast(tb200_ctx*, int on);
+/* Mod-q path only: share (in eighths, 0..8) of the 40-bit-prime limbs whose butterflies run on the FP64
+ * pipe (exact-integer doubles, 6 DFMA-class instructions per modular product) while the remaining limbs
+ * use the integer pipes; results are bit-identical for every share. */
+int tb200_ctx_set_f64_share(tb200_ctx*, int eighths);
 
 /* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */
 enum tb200_pw_op {

@@ -280,6 +280,17 @@ def check_he_ops(s: Setup, level=0):
     eq(h, out, eng.divide_by_p(d, level), "create_switcher_divide_by_p")
 
 
+# Internal-transform modes of the fused engine calls, all bit-identical by contract:
+# (mod-q path?, eighths of the 40-bit limbs on the FP64 pipe)
+ENGINE_MODES = ((False, 0), (True, 0), (True, 3), (True, 8))  # the default last
+
+
+def set_mode(s: "Setup", mode):
+    fast, share = mode
+    s.ctx.set_fast(fast)
+    s.ctx.set_f64_share(share)
+
+
 def check_engine(s: Setup, level: int, batch=None, ops=("rescale", "keyswitch", "switch_key", "rotate", "cc_mult",
                                                         "triplet", "pc_mult", "addsub")):
     h, o, eng, ctx = s.h, s.octx, s.eng, s.ctx

@@ -48,8 +48,8 @@ def test_pointwise_and_he_ops(h, logN, ns, K):
 def test_engine_every_level(h, logN, ns, K):
     s = Setup.toy(h, logN, ns, K, seed=200 + logN, rot_deltas=(1, 3))
     try:
-        for fast in (True, False):  # internal mod-q path / exact op kernels: same bits
-            s.ctx.set_fast(fast)
+        for mode in parity.ENGINE_MODES:  # internal mod-q path / exact op kernels: same bits
+            parity.set_mode(s, mode)
             for level in range(0, ns + 1):
                 parity.check_engine(s, level)
     finally:

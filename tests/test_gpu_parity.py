@@ -47,8 +47,8 @@ def test_toy_rings(h, logN, ns, K):
         parity.check_pointwise(s, min(1, ns), False)
         for level in range(0, ns + 1):
             parity.check_he_ops(s, level)
-            for fast in (True, False):  # internal mod-q path / exact op kernels: same bits
-                s.ctx.set_fast(fast)
+            for mode in parity.ENGINE_MODES:  # internal mod-q path / exact op kernels: same bits
+                parity.set_mode(s, mode)
                 parity.check_engine(s, level)
         s.ctx.set_chunk(2)
         parity.check_engine(s, 0, batch=3)
@@ -71,8 +71,8 @@ def test_preset_logN14(h):
         parity.check_pointwise(s, 0, True)
         for level in (0, 3, 6):
             parity.check_he_ops(s, level)
-            for fast in (True, False):
-                s.ctx.set_fast(fast)
+            for mode in parity.ENGINE_MODES:
+                parity.set_mode(s, mode)
                 parity.check_engine(s, level)
     finally:
         s.close()

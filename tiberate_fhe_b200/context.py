@@ -168,6 +168,10 @@ class Tb200Context:
         """Internal transforms of the fused engine calls: mod-q path (default) or exact op kernels."""
         self.lib.check(self.lib.tb200_ctx_set_fast(self.h, int(bool(on))), "set_fast")
 
+    def set_f64_share(self, eighths: int):
+        """Share (0..8 eighths) of the small-prime limbs transformed on the FP64 pipe (mod-q path)."""
+        self.lib.check(self.lib.tb200_ctx_set_f64_share(self.h, int(eighths)), "set_f64_share")
+
     # ---- level helpers -------------------------------------------------------------------
     def rows_at(self, level: int, with_special: bool = False) -> int:
         return (self.P if with_special else self.num_ordinary) - level

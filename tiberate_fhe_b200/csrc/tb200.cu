@@ -281,7 +281,9 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.ex_s = h_shoup(f.ex, qi);
       f.off = qi << (62 - h_bitlen(qi));
       f.small = (qi >> 42) == 0 ? 1 : 0;
-      f.pad = 0;
+      f.f64 = f.small;  // default: every 40-bit limb on the FP64 pipe (tb200_ctx_set_f64_share)
+      f.qd = (double)qi;
+      f.qinv = 1.0 / (double)qi;
     }
   }
   // rescale scales and P_k^-1 tables
@@ -401,7 +403,7 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
             upload(&c->d_ipsi4, ipsi4) == cudaSuccess && upload(&c->d_rescale, resc) == cudaSuccess &&
             upload(&c->d_pir, pir) == cudaSuccess && upload(&c->d_pir_sp, pirsp) == cudaSuccess &&
             upload(&c->d_lenter, lenter) == cudaSuccess && upload(&c->d_ks, c->ks) == cudaSuccess &&
-            upload(&c->d_fp, fps) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
+            ((c->fps = fps), upload(&c->d_fp, fps)) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
             upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
             upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
   if (!ok) {
@@ -453,6 +455,18 @@ extern "C" int tb200_ctx_set_chunk(tb200_ctx* c, int chunk) {
 extern "C" int tb200_ctx_set_fast(tb200_ctx* c, int on) {
   if (!c) return fail(TB200_EINVAL, "null context");
   c->fast = on != 0;
+  return 0;
+}
+
+// Share of the small-prime limbs (in eighths, 0..8) whose butterflies run on the FP64 pipe; the others
+// stay on the integer pipes, so co-resident CTAs of both kinds keep both pipes busy.
+extern "C" int tb200_ctx_set_f64_share(tb200_ctx* c, int eighths) {
+  if (!c || eighths < 0 || eighths > 8) return fail(TB200_EINVAL, "f64 share must be 0..8 (eighths)");
+  CK(cudaSetDevice(c->device));
+  c->f64_eighths = eighths;
+  for (int g = 0; g < c->P; ++g) c->fps[g].f64 = (c->fps[g].small && ((g * 5) & 7) < eighths) ? 1 : 0;
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(c->d_fp, c->fps.data(), sizeof(TbFastPrime) * c->P, cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -84,6 +84,8 @@ struct tb200_ctx {
   TbKsLevel* d_ks = nullptr; // [num_ord]
   // fast (mod-q) path tables
   int fast = 1;
+  int f64_eighths = 8;       // share (in eighths) of the small-prime limbs whose butterflies use the FP64 pipe
+  std::vector<TbFastPrime> fps;
   TbFastPrime* d_fp = nullptr;
   TbTw2 *d_tw = nullptr, *d_itw = nullptr;
   u64* d_resc3 = nullptr;    // [num_ord][P][3]: (q_l^-1 R mod q_g, Shoup companion, offset) per (level l, prime g)

@@ -11,6 +11,25 @@ struct TbDevFast {
   int logN, LA, LB, P;
 };
 
+// i64 tile <-> bit patterns of exact-integer doubles (FP64 butterfly policy)
+__device__ __forceinline__ void tile_to_f64(i64 (&x)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(__ll2double_rn(x[i]));
+}
+__device__ __forceinline__ void tile_from_f64(i64 (&x)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __double2ll_rn(__longlong_as_double(x[i]));
+}
+// reduce to [0, q) (forward pass B output / inverse exit) or to (-q/2-1, q/2+1) and back to integers
+__device__ __forceinline__ void tile_f64_reduce(i64 (&x)[16], const tb::FastF64Pol& p, bool canonical) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double r = p.reduce(__longlong_as_double(x[i]));
+    if (canonical) r = r < 0.0 ? __dadd_rn(r, p.q) : r;
+    x[i] = __double2ll_rn(r);
+  }
+}
+
 #define TB_FPRO_ENTER 0          // x = (a + q) * R                         (enter_ntt_radix2, mod q)
 #define TB_FPRO_RESCALE_ENTER 1  // x = ((a - r) q_l^-1 + [r > q_l/2]) * R  (rescale + enter, mod q)
 #define TB_FPRO_EXTEND 2         // x = sum_k d_k * (L_{k-1} R)             (ModUp extend, mod q)
@@ -122,10 +141,15 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a
   }
   auto slot = [&](int lx) { return tb::pad16((lx << a.LW) | col); };
   const TbTw2* tw = c.tw + ((long)g << c.logN);
-  if (P.small)
+  if (P.f64) {  // prologue values are lazy non-negative integers < 2^48: exact doubles
+    tile_to_f64(x);
+    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastF64Pol{P.qd, P.qinv}, slot);
+    tile_from_f64(x);  // signed, |x| < 2^48; pass B of the same limb takes the FP64 route as well
+  } else if (P.small) {
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-  else
+  } else {
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[(unsigned)tb::tile_x(tr, i, 0) << c.LB] = x[i];
 }
@@ -154,7 +178,12 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, 
     // round-0 layout: 16 consecutive threads read 16 consecutive residues (one 128-byte line)
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
-    if (P.small) {
+    if (P.f64) {
+      const tb::FastF64Pol pol{P.qd, P.qinv};
+      tile_to_f64(x);
+      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, pol, slot);
+      tile_f64_reduce(x, pol, true);  // [0, q)
+    } else if (P.small) {
       tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
     } else {
       tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
@@ -212,10 +241,16 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, 
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
-    if (P.small)
+    if (P.f64) {  // inputs in [0, 4q): after the LB stages < 2^(LB+2) q < 2^52; renormalised before the store
+      const tb::FastF64Pol pol{P.qd, P.qinv};
+      tile_to_f64(x);
+      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, pol, slot);
+      tile_f64_reduce(x, pol, false);
+    } else if (P.small) {
       tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-    else
+    } else {
       tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = x[i];
   }
@@ -237,6 +272,20 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
   for (int i = 0; i < 16; ++i) x[i] = s[(unsigned)tb::tile_x(tr, i, 0) << c.LB];
   auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
   const TbTw2* tw = c.itw + ((long)g << c.logN);
+  if (P.f64) {  // inputs |x| <= q/2 + 1 (renormalised by inverse pass B'): < 2^(LA-1) q after the LA stages
+    const tb::FastF64Pol pol{P.qd, P.qinv};
+    const double exd = __ull2double_rn(P.ex);
+    tile_to_f64(x);
+    tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, tw, pol, slot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double r = pol.mulmod(__longlong_as_double(x[i]), exd);  // x N^-1 R^-1, |r| <= q/2 + 1
+      r = r < 0.0 ? __dadd_rn(r, pol.q) : r;
+      r = r >= pol.q ? __dadd_rn(r, -pol.q) : r;
+      d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = __double2ll_rn(r);
+    }
+    return;
+  }
   if (P.small)
     tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
   else

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #define TB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #define TB_KERNEL_SHARED __shared__
+static __device__ __forceinline__ double tb_rint(double a) { return rint(a); }
 // streaming (L2-only) accesses for data that is touched once per kernel
 static __device__ __forceinline__ long tb_ldcg(const long* p) { return __ldcg(p); }
 static __device__ __forceinline__ longlong2 tb_ldcg2(const longlong2* p) { return __ldcg(p); }
@@ -53,6 +54,24 @@ static inline T __ldg(const T* p) {
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
   return (unsigned long long)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
 }
+#include <cmath>
+static inline double __longlong_as_double(long long v) {
+  double d;
+  std::memcpy(&d, &v, 8);
+  return d;
+}
+static inline long long __double_as_longlong(double d) {
+  long long v;
+  std::memcpy(&v, &d, 8);
+  return v;
+}
+static inline double __ll2double_rn(long long v) { return (double)v; }
+static inline double __ull2double_rn(unsigned long long v) { return (double)v; }
+static inline long long __double2ll_rn(double d) { return std::llrint(d); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline double tb_rint(double a) { return std::nearbyint(a); }
 static inline unsigned __umulhi(unsigned a, unsigned b) {
   return (unsigned)(((unsigned long long)a * b) >> 32);
 }
