@@ -13,7 +13,8 @@ import os
 MAX_GROUPS = 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtb200.so")
+# TB200_LIB: developer override used to A/B kernel build variants on the GPU box
+LIB_PATH = os.environ.get("TB200_LIB") or os.path.join(_HERE, "lib", "libtb200.so")
 
 
 class Poly(C.Structure):

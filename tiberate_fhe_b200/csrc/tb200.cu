@@ -127,6 +127,8 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   cudaFree(c->d_fp);
   cudaFree(c->d_tw);
   cudaFree(c->d_itw);
+  cudaFree(c->d_twd);
+  cudaFree(c->d_itwd);
   cudaFree(c->d_resc3);
   cudaFree(c->d_lenter2);
   cudaFree(c->d_bn);
@@ -284,6 +286,8 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.f64 = f.small;  // default: every 40-bit limb on the FP64 pipe (tb200_ctx_set_f64_share)
       f.qd = (double)qi;
       f.qinv = 1.0 / (double)qi;
+      f.exd = f.ex > qi / 2 ? -(double)(qi - f.ex) : (double)f.ex;
+      f.pad_ = 0.0;
     }
   }
   // rescale scales and P_k^-1 tables
@@ -397,6 +401,17 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
         }
     }
   }
+  // FP64 butterfly policy: the same tables as doubles centred into (-q/2, q/2]
+  std::vector<double> twd((size_t)P * N), itwd((size_t)P * N);
+  for (int g = 0; g < P; ++g) {
+    const u64 qi = (u64)q[g];
+    for (int i = 0; i < N; ++i) {
+      const size_t at = (size_t)g * N + i;
+      const u64 a = tw2[at].w, b = itw2[at].w;
+      twd[at] = a > qi / 2 ? -(double)(qi - a) : (double)a;
+      itwd[at] = b > qi / 2 ? -(double)(qi - b) : (double)b;
+    }
+  }
   if (lenter.empty()) lenter.push_back(0);
   if (lenter2.empty()) lenter2.push_back(0);
   bool ok = upload(&c->d_primes, c->primes) == cudaSuccess && upload(&c->d_psi4, psi4) == cudaSuccess &&
@@ -404,7 +419,8 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
             upload(&c->d_pir, pir) == cudaSuccess && upload(&c->d_pir_sp, pirsp) == cudaSuccess &&
             upload(&c->d_lenter, lenter) == cudaSuccess && upload(&c->d_ks, c->ks) == cudaSuccess &&
             ((c->fps = fps), upload(&c->d_fp, fps)) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
-            upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
+            upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_twd, twd) == cudaSuccess &&
+            upload(&c->d_itwd, itwd) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
             upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
   if (!ok) {
     fail(TB200_ENOMEM, "ctx_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -88,6 +88,7 @@ struct tb200_ctx {
   std::vector<TbFastPrime> fps;
   TbFastPrime* d_fp = nullptr;
   TbTw2 *d_tw = nullptr, *d_itw = nullptr;
+  double *d_twd = nullptr, *d_itwd = nullptr;  // centred double twiddles, same layout
   u64* d_resc3 = nullptr;    // [num_ord][P][3]: (q_l^-1 R mod q_g, Shoup companion, offset) per (level l, prime g)
   u64* d_bn = nullptr;       // ModDown: [(K+1)][P][2] (-B_k mod q, Shoup) k < K, then (B_{K-1}, Shoup)
   u64* d_lenter2 = nullptr;  // (L_{k-1} R mod q_g, Shoup companion) pairs, same indexing as d_lenter
@@ -98,6 +99,8 @@ struct tb200_ctx {
     d.fp = d_fp;
     d.tw = d_tw;
     d.itw = d_itw;
+    d.twd = d_twd;
+    d.itwd = d_itwd;
     d.logN = logN;
     d.LA = LA;
     d.LB = LB;

@@ -31,6 +31,7 @@ struct __align__(16) TbFastPrime {
   int small;         // q < 2^42
   int f64;           // small prime whose butterflies run on the FP64 pipe (see FastF64Pol)
   double qd, qinv;   // q and 1/q as doubles
+  double exd, pad_;  // ex centred into (-q/2, q/2]
 };
 
 namespace tb {
@@ -83,36 +84,47 @@ struct FastSmallPol {
 };
 
 // q < 2^42 on the FP64 pipe.  B200 issues 64 DFMA/clk/SM on a pipe the integer butterflies leave idle;
-// a modular product of an exact-integer double a (|a| < 2^51) with a twiddle w < 2^42 is
-//     h = a*w (rounded), l = fma(a, w, -h) (the exact rounding error), c = rint(h/q),
-//     r = fma(-c, q, h) + l            -- exact: h - c q and l are integers below 2^44 --
-// giving r = a w - c q with |r| < 1.5 q: 6 FP64 instructions, signed residues, no conditional
-// subtraction.  Measured (tools/ubench_modmul.cu): 1.33 T butterflies/s against 0.78 T/s for the integer
-// Shoup butterfly.  Registers hold the doubles' bit patterns in the i64 tile, so the tiling, the
-// shared-memory exchanges and the twiddle tables (plain twiddle converted on load) are shared.
-// Bounds: forward values grow by < 1.5q per stage (< 2^46 after 17 stages); inverse values double per
+// a modular product of an exact-integer double a (|a| <= 2^52) with a centred twiddle |w| <= q/2 is
+//     h = a*w (rounded), l = fma(a, w, -h) (the exact rounding error),
+//     c = (h/q + M) - M  with M = 1.5 * 2^52  (round-to-integer on the FP64 pipe: |h/q| <= 2^51, so
+//                                              h/q + M lies in [2^52, 2^53] where doubles are integers),
+//     r = fma(-c, q, h) + l            -- exact: h - c q and l are integers far below 2^53 --
+// giving r = a w - c q with |r| < 1.1 q: 6 FP64 instructions, signed residues, no conditional
+// subtraction, nothing on the XU pipe (rint / int<->double conversions would go there).  Measured
+// (tools/ubench_modmul.cu): 1.33 T butterflies/s against 0.78 T/s for the integer Shoup butterfly.
+// Registers hold the doubles' bit patterns in the i64 tile, so the tiling and the shared-memory
+// exchanges are shared; the twiddles come from a table of centred doubles in the same layout.
+// Bounds: forward values grow by < 1.1q per stage (< 2^49 after 17 stages); inverse values double per
 // stage, so the inverse kernels renormalise once per pass (8-9 stages: < 2^52).
+#define TB_F64_MAGIC 6755399441055744.0        // 1.5 * 2^52
+#define TB_F64_MAGIC_BITS 0x4338000000000000ll  // its bit pattern
 struct FastF64Pol {
   double q, qinv;
-  typedef TbTw2 TW;
-  static __device__ __forceinline__ TW load(const TW* t) { return load_tw2(t); }
+  typedef double TW;
+  static __device__ __forceinline__ TW load(const TW* t) { return __ldg(t); }
+  static __device__ __forceinline__ double round_int(double x_plus_magic) { return __dadd_rn(x_plus_magic, -TB_F64_MAGIC); }
+  // exact integer (|x| < 2^51) <-> double without the conversion unit
+  static __device__ __forceinline__ double from_int(i64 x) {
+    return __dadd_rn(__longlong_as_double(x + TB_F64_MAGIC_BITS), -TB_F64_MAGIC);
+  }
+  static __device__ __forceinline__ i64 to_int(double d) {
+    return __double_as_longlong(__dadd_rn(d, TB_F64_MAGIC)) - TB_F64_MAGIC_BITS;
+  }
   __device__ __forceinline__ double mulmod(double a, double w) const {
     const double h = __dmul_rn(a, w);
     const double l = __fma_rn(a, w, -h);
-    const double c = tb_rint(__dmul_rn(h, qinv));
+    const double c = round_int(__fma_rn(h, qinv, TB_F64_MAGIC));
     return __dadd_rn(__fma_rn(-c, q, h), l);
   }
-  __device__ __forceinline__ double reduce(double a) const {  // -> (-q/2 - 1, q/2 + 1)
-    return __fma_rn(-tb_rint(__dmul_rn(a, qinv)), q, a);
+  __device__ __forceinline__ double reduce(double a) const {  // -> [-q/2 - 1, q/2 + 1]
+    return __fma_rn(-round_int(__fma_rn(a, qinv, TB_F64_MAGIC)), q, a);
   }
-  __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
-    const double w = __ull2double_rn(S.w);
+  __device__ __forceinline__ void ct(i64& U, i64& O, TW w, int) const {
     const double u = __longlong_as_double(U), v = mulmod(__longlong_as_double(O), w);
     U = __double_as_longlong(__dadd_rn(u, v));
     O = __double_as_longlong(__dadd_rn(u, -v));
   }
-  __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int) const {
-    const double w = __ull2double_rn(S.w);
+  __device__ __forceinline__ void gs(i64& U, i64& V, TW w, int) const {
     const double u = __longlong_as_double(U), v = __longlong_as_double(V);
     U = __double_as_longlong(__dadd_rn(u, v));
     V = __double_as_longlong(mulmod(__dadd_rn(u, -v), w));

@@ -8,25 +8,28 @@ struct TbDevFast {
   const TbFastPrime* fp;  // [P]
   const TbTw2* tw;        // [P][N] forward twiddles (plain + Shoup)
   const TbTw2* itw;       // [P][N] inverse twiddles
+  const double *twd, *itwd;  // the same twiddles as centred doubles (FP64 butterfly policy)
   int logN, LA, LB, P;
 };
 
 // i64 tile <-> bit patterns of exact-integer doubles (FP64 butterfly policy)
 __device__ __forceinline__ void tile_to_f64(i64 (&x)[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(__ll2double_rn(x[i]));
+  for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(tb::FastF64Pol::from_int(x[i]));
 }
-__device__ __forceinline__ void tile_from_f64(i64 (&x)[16]) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = __double2ll_rn(__longlong_as_double(x[i]));
-}
-// reduce to [0, q) (forward pass B output / inverse exit) or to (-q/2-1, q/2+1) and back to integers
-__device__ __forceinline__ void tile_f64_reduce(i64 (&x)[16], const tb::FastF64Pol& p, bool canonical) {
+// reduce to [0, q) as integers (forward pass B output) or to [-q/2-1, q/2+1] kept as doubles (the
+// intermediate between the two inverse passes)
+template <bool CANONICAL_INT>
+__device__ __forceinline__ void tile_f64_reduce(i64 (&x)[16], const tb::FastF64Pol& p) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     double r = p.reduce(__longlong_as_double(x[i]));
-    if (canonical) r = r < 0.0 ? __dadd_rn(r, p.q) : r;
-    x[i] = __double2ll_rn(r);
+    if constexpr (CANONICAL_INT) {
+      r = r < 0.0 ? __dadd_rn(r, p.q) : r;
+      x[i] = tb::FastF64Pol::to_int(r);
+    } else {
+      x[i] = __double_as_longlong(r);
+    }
   }
 }
 
@@ -108,8 +111,11 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
 }
 
 // forward pass A with a fused prologue.  EXTEND: grid.z = batch * ngroups, dst batch index = grid.z.
+#ifndef TB_EXT_MINB
+#define TB_EXT_MINB 3
+#endif
 template <int LA, int PRO>
-__global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
+__global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int W = 1 << a.LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> a.LW;
@@ -143,8 +149,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a
   const TbTw2* tw = c.tw + ((long)g << c.logN);
   if (P.f64) {  // prologue values are lazy non-negative integers < 2^48: exact doubles
     tile_to_f64(x);
-    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastF64Pol{P.qd, P.qinv}, slot);
-    tile_from_f64(x);  // signed, |x| < 2^48; pass B of the same limb takes the FP64 route as well
+    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.twd + ((long)g << c.logN), tb::FastF64Pol{P.qd, P.qinv}, slot);
+    // stored as doubles (|x| < 2^49): pass B of the same limb takes the FP64 route as well
   } else if (P.small) {
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
   } else {
@@ -180,9 +186,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, 
     for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
     if (P.f64) {
       const tb::FastF64Pol pol{P.qd, P.qinv};
-      tile_to_f64(x);
-      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, pol, slot);
-      tile_f64_reduce(x, pol, true);  // [0, q)
+      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.twd + ((long)g << c.logN), pol, slot);  // doubles from pass A
+      tile_f64_reduce<true>(x, pol);  // [0, q)
     } else if (P.small) {
       tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
     } else {
@@ -244,8 +249,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, 
     if (P.f64) {  // inputs in [0, 4q): after the LB stages < 2^(LB+2) q < 2^52; renormalised before the store
       const tb::FastF64Pol pol{P.qd, P.qinv};
       tile_to_f64(x);
-      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, pol, slot);
-      tile_f64_reduce(x, pol, false);
+      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, c.itwd + ((long)g << c.logN), pol, slot);
+      tile_f64_reduce<false>(x, pol);  // stays double for pass A'
     } else if (P.small) {
       tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
     } else {
@@ -274,15 +279,13 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
   const TbTw2* tw = c.itw + ((long)g << c.logN);
   if (P.f64) {  // inputs |x| <= q/2 + 1 (renormalised by inverse pass B'): < 2^(LA-1) q after the LA stages
     const tb::FastF64Pol pol{P.qd, P.qinv};
-    const double exd = __ull2double_rn(P.ex);
-    tile_to_f64(x);
-    tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, tw, pol, slot);
+    tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, c.itwd + ((long)g << c.logN), pol, slot);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      double r = pol.mulmod(__longlong_as_double(x[i]), exd);  // x N^-1 R^-1, |r| <= q/2 + 1
+      double r = pol.mulmod(__longlong_as_double(x[i]), P.exd);  // x N^-1 R^-1, |r| < 1.1 q
       r = r < 0.0 ? __dadd_rn(r, pol.q) : r;
       r = r >= pol.q ? __dadd_rn(r, -pol.q) : r;
-      d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = __double2ll_rn(r);
+      d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = tb::FastF64Pol::to_int(r);
     }
     return;
   }
