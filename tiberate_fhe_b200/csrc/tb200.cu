@@ -368,6 +368,9 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       fill[owner] += alpha;
       G.src_prime0 = -1;
       G.src_row0 = -1;
+      G.wide_mask = 0;
+      for (int k = 0; k < alpha; ++k)
+        if (((u64)qg[alive[k]] >> 42) != 0) G.wide_mask |= 1 << k;
       if (owner == rank) {
         int li = 0;
         while (ord_gid[li] != alive[0]) ++li;

@@ -336,7 +336,7 @@ struct TbKsGroup {       // one digit group at one level
   int gid;               // global group id (index into the key-switch key)
   int src_row0;          // owner only: row of the group's first prime inside the (local) input tensor, else -1
   int src_prime0;        // owner only: index of that prime in the context's prime table
-  int pad;
+  int wide_mask;         // bit k: the group's k-th alive prime is >= 2^42 (its digits do not fit a double)
   long lenter_off;       // offset of this group's L_enter block [(alpha-1)][P] in TbKsTables.lenter
   i64 Y[TB_MAXA];        // Y[i] = (L_i^-1 mod m_{i+1}) R mod m_{i+1}
   i64 Lsc[TB_MAXA][TB_MAXA];  // Lsc[i][j] = L_i R mod m_j for j >= i+2

@@ -110,6 +110,49 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
   }
 }
 
+// The same sums on the FP64 pipe, for a target limb that takes the FP64 butterflies: a digit of a
+// 40-bit source prime is a signed integer below 2^42 (a Montgomery product of k_digits) and enters
+// FastF64Pol::mulmod directly; a digit of a 60-bit source prime is split as hi * 2^30 + lo.  Every
+// term is below 1.1 q in magnitude, so |x| < 2 (alpha + 1) q < 2^47; x stays a double for the stages.
+// Digit-major: one constant live at a time, 8 loads in flight per thread.
+__device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAArgs& a, const TbFastPrime& P,
+                                                    const TbKsGroup& G, int bt, int g, int nP, int tr, int f0, int LB,
+                                                    unsigned c0) {
+  const tb::FastF64Pol pol{P.qd, P.qinv};
+  double v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.0;
+  const u64* le = a.lenter2 + 2 * (G.lenter_off + g);
+  const i64* row = a.src.row(bt, G.state_row0) + c0;
+  u64 ck = P.Rm;
+  for (int k = 0; k < G.alpha; ++k) {
+    const double C = tb::FastF64Pol::from_int(ck > (P.q >> 1) ? (i64)ck - (i64)P.q : (i64)ck);
+    const bool wide = (G.wide_mask >> k) & 1;
+    const double C30 = wide ? pol.mulmod(C, 1073741824.0) : 0.0;
+#pragma unroll
+    for (int h = 0; h < 16; h += 8) {
+      i64 d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = row[(unsigned)tb::tile_x(tr, h + i, f0) << LB];
+      if (wide) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double hi = tb::FastF64Pol::from_int(d[i] >> 30), lo = tb::FastF64Pol::from_int(d[i] & 0x3fffffffll);
+          v[h + i] = __dadd_rn(v[h + i], __dadd_rn(pol.mulmod(hi, C30), pol.mulmod(lo, C)));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[h + i] = __dadd_rn(v[h + i], pol.mulmod(tb::FastF64Pol::from_int(d[i]), C));
+      }
+    }
+    if (k + 1 < G.alpha) ck = le[0];  // (L_k R mod q_g) for the next digit
+    le += 2 * nP;
+    row += a.src.rs;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(v[i]);
+}
+
 // forward pass A with a fused prologue.  EXTEND: grid.z = batch * ngroups, dst batch index = grid.z.
 #ifndef TB_EXT_MINB
 #define TB_EXT_MINB 3
@@ -132,13 +175,17 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   i64 x[16];
   if constexpr (PRO == TB_FPRO_EXTEND) {
     const TbKsGroup& G = a.lv->g[gi];
-    switch (G.alpha) {
+    if (P.f64) {
+      extend_prologue_f64(x, a, P, G, bt, g, c.P, tr, f0, c.LB, c0);
+    } else {
+      switch (G.alpha) {
 #define XCASE(n) \
   case n:        \
     extend_prologue<n>(x, a, P, G, bt, g, c.P, tr, f0, c.LB, c0); \
     break;
-      XCASE(1) XCASE(2) XCASE(3) XCASE(4) XCASE(5) XCASE(6) XCASE(7) XCASE(8)
+        XCASE(1) XCASE(2) XCASE(3) XCASE(4) XCASE(5) XCASE(6) XCASE(7) XCASE(8)
 #undef XCASE
+      }
     }
   } else {
 #pragma unroll
@@ -147,8 +194,8 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   }
   auto slot = [&](int lx) { return tb::pad16((lx << a.LW) | col); };
   const TbTw2* tw = c.tw + ((long)g << c.logN);
-  if (P.f64) {  // prologue values are lazy non-negative integers < 2^48: exact doubles
-    tile_to_f64(x);
+  if (P.f64) {  // integer prologues give lazy non-negative values < 2^48: exact doubles
+    if constexpr (PRO != TB_FPRO_EXTEND) tile_to_f64(x);
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.twd + ((long)g << c.logN), tb::FastF64Pol{P.qd, P.qinv}, slot);
     // stored as doubles (|x| < 2^49): pass B of the same limb takes the FP64 route as well
   } else if (P.small) {
