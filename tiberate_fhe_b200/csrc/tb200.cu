@@ -131,6 +131,7 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   cudaFree(c->d_itwd);
   cudaFree(c->d_resc3);
   cudaFree(c->d_lenter2);
+  cudaFree(c->d_lenterd);
   cudaFree(c->d_bn);
   cudaFree(c->ws);
   delete c;
@@ -287,7 +288,10 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.qd = (double)qi;
       f.qinv = 1.0 / (double)qi;
       f.exd = f.ex > qi / 2 ? -(double)(qi - f.ex) : (double)f.ex;
-      f.pad_ = 0.0;
+      {
+        const u64 ninv = h_invmod_prime((u64)N, qi);
+        f.exNd = ninv > qi / 2 ? -(double)(qi - ninv) : (double)ninv;
+      }
     }
   }
   // rescale scales and P_k^-1 tables
@@ -333,6 +337,7 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
   // digit groups per level
   std::vector<i64> lenter;
   std::vector<u64> lenter2;
+  std::vector<double> lenterd;  // L_{k-1} mod q_g centred, as doubles (FP64 extend: no Montgomery factor)
   c->ks.resize(no_g);
   for (int l = 0; l < no_g; ++l) {
     TbKsLevel& lv = c->ks[l];
@@ -401,6 +406,8 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
           const u64 C = h_mulmod(Lmod(i, qq), (u64)(Rbig % qq), qq);
           lenter2.push_back(C);
           lenter2.push_back(h_shoup(C, qq));
+          const u64 Lq = Lmod(i, qq);
+          lenterd.push_back(Lq > qq / 2 ? -(double)(qq - Lq) : (double)Lq);
         }
     }
   }
@@ -417,6 +424,7 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
   }
   if (lenter.empty()) lenter.push_back(0);
   if (lenter2.empty()) lenter2.push_back(0);
+  if (lenterd.empty()) lenterd.push_back(0.0);
   bool ok = upload(&c->d_primes, c->primes) == cudaSuccess && upload(&c->d_psi4, psi4) == cudaSuccess &&
             upload(&c->d_ipsi4, ipsi4) == cudaSuccess && upload(&c->d_rescale, resc) == cudaSuccess &&
             upload(&c->d_pir, pir) == cudaSuccess && upload(&c->d_pir_sp, pirsp) == cudaSuccess &&
@@ -424,7 +432,7 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
             ((c->fps = fps), upload(&c->d_fp, fps)) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
             upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_twd, twd) == cudaSuccess &&
             upload(&c->d_itwd, itwd) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
-            upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
+            upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_lenterd, lenterd) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
   if (!ok) {
     fail(TB200_ENOMEM, "ctx_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     tb200_ctx_destroy(c);
@@ -745,14 +753,14 @@ static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gri
   return 0;
 }
 static int launch_fast_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
-                             tb200_stream st) {
+                             int mac_chain, tb200_stream st) {
   const int lw = ntt_lw(c);
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
   switch (c->LA) {
 #define ACASE(n)                                                                        \
   case n: {                                                                             \
     auto kfn = k_fast_inv_A<n>;                                                         \
-    LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw);     \
+    LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw, mac_chain);     \
   } break;
     ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
 #undef ACASE
@@ -808,11 +816,13 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
   if (rc) return rc;
   return launch_fast_B(c, false, dst, dst, rows, batch, prime0, st);
 }
+// mac_chain: the input is the key inner product of an FP64-extended digit expansion, whose FP64 limbs
+// carry no Montgomery factor (extend_prologue_f64): their exit multiplies by N^-1 instead of N^-1 R^-1
 static int fast_inverse_exit(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
-                             tb200_stream st) {
+                             tb200_stream st, int mac_chain = 0) {
   int rc = launch_fast_B(c, true, src, dst, rows, batch, prime0, st);
   if (rc) return rc;
-  return launch_fast_inv_A(c, dst, dst, rows, batch, prime0, st);
+  return launch_fast_inv_A(c, dst, dst, rows, batch, prime0, mac_chain, st);
 }
 
 // ---- fused HE ops ---------------------------------------------------------------------------------
@@ -998,6 +1008,7 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     fa.dst = dense(ext, E, N);
     fa.lv = dlv;
     fa.lenter2 = c->d_lenter2;
+    fa.lenterd = c->d_lenterd;
     fa.prime0 = p0;
     fa.ngroups = ng;
     if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) return rc;
@@ -1006,7 +1017,7 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),
            dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb);
     // back to coefficients, canonical
-    if ((rc = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, st))) return rc;
+    if ((rc = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, st, 1))) return rc;
   } else {
     LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
            dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, state, ext, p0, N, E);

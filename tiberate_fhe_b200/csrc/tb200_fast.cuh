@@ -31,7 +31,7 @@ struct __align__(16) TbFastPrime {
   int small;         // q < 2^42
   int f64;           // small prime whose butterflies run on the FP64 pipe (see FastF64Pol)
   double qd, qinv;   // q and 1/q as doubles
-  double exd, pad_;  // ex centred into (-q/2, q/2]
+  double exd, exNd;  // ex and N^-1 mod q centred into (-q/2, q/2]
 };
 
 namespace tb {

@@ -43,6 +43,7 @@ struct TbFwdAArgs {
   i64 round_at;           // RESCALE_ENTER: q_l / 2
   const TbKsLevel* lv;    // EXTEND
   const u64* lenter2;     // EXTEND: (C, C') pairs, indexed (G.lenter_off + (k-1) P + prime)
+  const double* lenterd;  // EXTEND, FP64 limbs: L_{k-1} mod q centred (no Montgomery factor), same indexing
   int prime0, LW, ngroups;
 };
 
@@ -110,24 +111,28 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
   }
 }
 
-// The same sums on the FP64 pipe, for a target limb that takes the FP64 butterflies: a digit of a
-// 40-bit source prime is a signed integer below 2^42 (a Montgomery product of k_digits) and enters
-// FastF64Pol::mulmod directly; a digit of a 60-bit source prime is split as hi * 2^30 + lo.  Every
-// term is below 1.1 q in magnitude, so |x| < 2 (alpha + 1) q < 2^47; x stays a double for the stages.
+// The same sums on the FP64 pipe, for a target limb that takes the FP64 butterflies -- WITHOUT the
+// Montgomery factor: x = d_0 + sum_{k>=1} d_k L_{k-1} mod q, so the first digit costs no product.
+// (The key inner product then yields x key instead of x key R, and k_fast_inv_A's exit multiplies
+// these limbs by N^-1 instead of N^-1 R^-1: `mac_chain`.)  A digit of a 40-bit source prime is a
+// signed integer below 2^42 (a Montgomery product of k_digits) and enters FastF64Pol::mulmod directly;
+// a digit of a 60-bit source prime is split as hi * 2^30 + lo.  Every term is below max(2^42, 1.1 q)
+// in magnitude, so |x| < 2^47; x stays a double for the stages.
 // Digit-major: one constant live at a time, 8 loads in flight per thread.
 __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAArgs& a, const TbFastPrime& P,
                                                     const TbKsGroup& G, int bt, int g, int nP, int tr, int f0, int LB,
                                                     unsigned c0) {
   const tb::FastF64Pol pol{P.qd, P.qinv};
   double v[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = 0.0;
-  const u64* le = a.lenter2 + 2 * (G.lenter_off + g);
+  const double* le = a.lenterd + (G.lenter_off + g);
   const i64* row = a.src.row(bt, G.state_row0) + c0;
-  u64 ck = P.Rm;
   for (int k = 0; k < G.alpha; ++k) {
-    const double C = tb::FastF64Pol::from_int(ck > (P.q >> 1) ? (i64)ck - (i64)P.q : (i64)ck);
     const bool wide = (G.wide_mask >> k) & 1;
+    double C = 1.0;
+    if (k > 0) {
+      C = le[0];
+      le += nP;
+    }
     const double C30 = wide ? pol.mulmod(C, 1073741824.0) : 0.0;
 #pragma unroll
     for (int h = 0; h < 16; h += 8) {
@@ -138,15 +143,17 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const double hi = tb::FastF64Pol::from_int(d[i] >> 30), lo = tb::FastF64Pol::from_int(d[i] & 0x3fffffffll);
-          v[h + i] = __dadd_rn(v[h + i], __dadd_rn(pol.mulmod(hi, C30), pol.mulmod(lo, C)));
+          const double t = __dadd_rn(pol.mulmod(hi, C30), k == 0 ? lo : pol.mulmod(lo, C));
+          v[h + i] = k == 0 ? t : __dadd_rn(v[h + i], t);
         }
+      } else if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[h + i] = tb::FastF64Pol::from_int(d[i]);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[h + i] = __dadd_rn(v[h + i], pol.mulmod(tb::FastF64Pol::from_int(d[i]), C));
       }
     }
-    if (k + 1 < G.alpha) ck = le[0];  // (L_k R mod q_g) for the next digit
-    le += 2 * nP;
     row += a.src.rs;
   }
 #pragma unroll
@@ -310,7 +317,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, 
 
 // inverse pass A' + exit: y = CS1(x * N^-1 R^-1)  == intt_radix2_exit_reduce of the reference (canonical).
 template <int LA>
-__global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LW) {
+__global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LW,
+                                                       int mac_chain) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
@@ -327,9 +335,10 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
   if (P.f64) {  // inputs |x| <= q/2 + 1 (renormalised by inverse pass B'): < 2^(LA-1) q after the LA stages
     const tb::FastF64Pol pol{P.qd, P.qinv};
     tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, c.itwd + ((long)g << c.logN), pol, slot);
+    const double exd = mac_chain ? P.exNd : P.exd;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      double r = pol.mulmod(__longlong_as_double(x[i]), P.exd);  // x N^-1 R^-1, |r| < 1.1 q
+      double r = pol.mulmod(__longlong_as_double(x[i]), exd);  // x N^-1 R^-1, |r| < 1.1 q
       r = r < 0.0 ? __dadd_rn(r, pol.q) : r;
       r = r >= pol.q ? __dadd_rn(r, -pol.q) : r;
       d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = tb::FastF64Pol::to_int(r);
@@ -376,12 +385,32 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
   const int ng = lv->ngroups;
   longlong2 o0, o1;
   if (small) {
+    // lazy residue (< 2^49) times key residue (|k| < 2^42): |term| < 2^91, the sum over <= 32 groups fits 128 bits.
+    // Two digit groups per iteration so that six 16-byte loads are in flight per thread (the kernel
+    // is latency-bound: ncu long_scoreboard 5.6 stalls per issue before the unroll)
     __int128 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
-    for (int gi = 0; gi < ng; ++gi) {
+    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + j;
+    const long estride = (long)rowsE * N, koff = (long)(level + t) * key.rs + j;
+    int gi = 0;
+    for (; gi + 2 <= ng; gi += 2) {
+      const int g0 = lv->g[gi].gid, g1 = lv->g[gi + 1].gid;
+      const longlong2 e0 = *reinterpret_cast<const longlong2*>(ep);
+      const longlong2 e1 = *reinterpret_cast<const longlong2*>(ep + estride);
+      const longlong2 kb0 = *reinterpret_cast<const longlong2*>(key.b[g0] + koff);
+      const longlong2 ka0 = *reinterpret_cast<const longlong2*>(key.a[g0] + koff);
+      const longlong2 kb1 = *reinterpret_cast<const longlong2*>(key.b[g1] + koff);
+      const longlong2 ka1 = *reinterpret_cast<const longlong2*>(key.a[g1] + koff);
+      ep += 2 * estride;
+      a0x += (__int128)e0.x * kb0.x + (__int128)e1.x * kb1.x;
+      a0y += (__int128)e0.y * kb0.y + (__int128)e1.y * kb1.y;
+      a1x += (__int128)e0.x * ka0.x + (__int128)e1.x * ka1.x;
+      a1y += (__int128)e0.y * ka0.y + (__int128)e1.y * ka1.y;
+    }
+    if (gi < ng) {
       const int gid = lv->g[gi].gid;
-      const longlong2 e = *reinterpret_cast<const longlong2*>(ext + (((long)bt * ng + gi) * rowsE + t) * N + j);
-      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + (long)(level + t) * key.rs + j);
-      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + (long)(level + t) * key.rs + j);
+      const longlong2 e = *reinterpret_cast<const longlong2*>(ep);
+      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + koff);
+      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + koff);
       a0x += (__int128)e.x * kb.x;
       a0y += (__int128)e.y * kb.y;
       a1x += (__int128)e.x * ka.x;
