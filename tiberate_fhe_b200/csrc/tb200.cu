@@ -739,16 +739,18 @@ static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gri
   const int lw = ntt_lw(c);
   a.LW = lw;
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)gridz), block(1u << (c->LA - 4 + lw));
-  switch (c->LA) {
-#define ACASE(n)                                                        \
-  case n: {                                                             \
-    auto kfn = k_fast_fwd_A<n, PRO>;                                    \
+  const bool big = c->LB == 8 && lw == 12 - c->LA;  // logN >= 12: compile-time strides
+  switch (c->LA + (big ? 100 : 0)) {
+#define ACASE(n, B)                                                     \
+  case n + (B ? 100 : 0): {                                             \
+    auto kfn = k_fast_fwd_A<n, PRO, B>;                                 \
     LAUNCHN("k_fast_fwd_A", kfn, grid, block, st, c->devf(), a);        \
   } break;
-    ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
+    ACASE(4, false) ACASE(5, false) ACASE(6, false)
+    ACASE(4, true) ACASE(5, true) ACASE(6, true) ACASE(7, true) ACASE(8, true) ACASE(9, true)
 #undef ACASE
     default:
-      return fail(TB200_EINVAL, "unsupported LA %d", c->LA);
+      return fail(TB200_EINVAL, "unsupported LA %d (LB %d)", c->LA, c->LB);
   }
   return 0;
 }
@@ -756,16 +758,18 @@ static int launch_fast_inv_A(const tb200_ctx* c, TbView src, TbView dst, int row
                              int mac_chain, tb200_stream st) {
   const int lw = ntt_lw(c);
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
-  switch (c->LA) {
-#define ACASE(n)                                                                        \
-  case n: {                                                                             \
-    auto kfn = k_fast_inv_A<n>;                                                         \
-    LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw, mac_chain);     \
+  const bool big = c->LB == 8 && lw == 12 - c->LA;
+  switch (c->LA + (big ? 100 : 0)) {
+#define ACASE(n, B)                                                                            \
+  case n + (B ? 100 : 0): {                                                                    \
+    auto kfn = k_fast_inv_A<n, B>;                                                             \
+    LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw, mac_chain); \
   } break;
-    ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
+    ACASE(4, false) ACASE(5, false) ACASE(6, false)
+    ACASE(4, true) ACASE(5, true) ACASE(6, true) ACASE(7, true) ACASE(8, true) ACASE(9, true)
 #undef ACASE
     default:
-      return fail(TB200_EINVAL, "unsupported LA %d", c->LA);
+      return fail(TB200_EINVAL, "unsupported LA %d (LB %d)", c->LA, c->LB);
   }
   return 0;
 }

@@ -104,11 +104,14 @@ struct FastF64Pol {
   static __device__ __forceinline__ TW load(const TW* t) { return __ldg(t); }
   static __device__ __forceinline__ double round_int(double x_plus_magic) { return __dadd_rn(x_plus_magic, -TB_F64_MAGIC); }
   // exact integer (|x| < 2^51) <-> double without the conversion unit
+  // (the magic's low word is zero: one 32-bit add on the high word)
   static __device__ __forceinline__ double from_int(i64 x) {
-    return __dadd_rn(__longlong_as_double(x + TB_F64_MAGIC_BITS), -TB_F64_MAGIC);
+    const u64 b = ((u64)((unsigned)((u64)x >> 32) + 0x43380000u) << 32) | (unsigned)x;
+    return __dadd_rn(__longlong_as_double((i64)b), -TB_F64_MAGIC);
   }
   static __device__ __forceinline__ i64 to_int(double d) {
-    return __double_as_longlong(__dadd_rn(d, TB_F64_MAGIC)) - TB_F64_MAGIC_BITS;
+    const u64 b = (u64)__double_as_longlong(__dadd_rn(d, TB_F64_MAGIC));
+    return (i64)(((u64)((unsigned)(b >> 32) - 0x43380000u) << 32) | (unsigned)b);
   }
   __device__ __forceinline__ double mulmod(double a, double w) const {
     const double h = __dmul_rn(a, w);

@@ -164,11 +164,15 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
 #ifndef TB_EXT_MINB
 #define TB_EXT_MINB 3
 #endif
-template <int LA, int PRO>
+// BIG: logN >= 12, where LB = 8 and the column width is 2^(12 - LA): strides, shared-memory slots and
+// load/store offsets become immediates (ncu: half of the instructions of the runtime-LB build were
+// address arithmetic).
+template <int LA, int PRO, bool BIG>
 __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
-  const int W = 1 << a.LW;
-  const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> a.LW;
+  const int LB = BIG ? 8 : c.LB, LW = BIG ? 12 - LA : a.LW;
+  const int W = 1 << LW;
+  const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
   const int limb = blockIdx.y, g = a.prime0 + limb;
   const TbFastPrime P = c.fp[g];
   int bt = blockIdx.z, gi = 0;
@@ -183,12 +187,12 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   if constexpr (PRO == TB_FPRO_EXTEND) {
     const TbKsGroup& G = a.lv->g[gi];
     if (P.f64) {
-      extend_prologue_f64(x, a, P, G, bt, g, c.P, tr, f0, c.LB, c0);
+      extend_prologue_f64(x, a, P, G, bt, g, c.P, tr, f0, LB, c0);
     } else {
       switch (G.alpha) {
 #define XCASE(n) \
   case n:        \
-    extend_prologue<n>(x, a, P, G, bt, g, c.P, tr, f0, c.LB, c0); \
+    extend_prologue<n>(x, a, P, G, bt, g, c.P, tr, f0, LB, c0); \
     break;
         XCASE(1) XCASE(2) XCASE(3) XCASE(4) XCASE(5) XCASE(6) XCASE(7) XCASE(8)
 #undef XCASE
@@ -197,9 +201,9 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((unsigned)tb::tile_x(tr, i, f0) << c.LB) + c0, g, c.P);
+      x[i] = fast_prologue<PRO>(a, P, bt, gi, limb, ((unsigned)tb::tile_x(tr, i, f0) << LB) + c0, g, c.P);
   }
-  auto slot = [&](int lx) { return tb::pad16((lx << a.LW) | col); };
+  auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
   const TbTw2* tw = c.tw + ((long)g << c.logN);
   if (P.f64) {  // integer prologues give lazy non-negative values < 2^48: exact doubles
     if constexpr (PRO != TB_FPRO_EXTEND) tile_to_f64(x);
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
   }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) d[(unsigned)tb::tile_x(tr, i, 0) << c.LB] = x[i];
+  for (int i = 0; i < 16; ++i) d[(unsigned)tb::tile_x(tr, i, 0) << LB] = x[i];
 }
 
 // forward pass B; outputs: small primes < 72q, other primes reduced to [0, 2q).
@@ -316,10 +320,11 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, 
 }
 
 // inverse pass A' + exit: y = CS1(x * N^-1 R^-1)  == intt_radix2_exit_reduce of the reference (canonical).
-template <int LA>
-__global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LW,
+template <int LA, bool BIG>
+__global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LWr,
                                                        int mac_chain) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int LB = BIG ? 8 : c.LB, LW = BIG ? 12 - LA : LWr;
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
   constexpr int f0 = tb::fwd_field<LA>(0);
   i64 x[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = s[(unsigned)tb::tile_x(tr, i, 0) << c.LB];
+  for (int i = 0; i < 16; ++i) x[i] = s[(unsigned)tb::tile_x(tr, i, 0) << LB];
   auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
   const TbTw2* tw = c.itw + ((long)g << c.logN);
   if (P.f64) {  // inputs |x| <= q/2 + 1 (renormalised by inverse pass B'): < 2^(LA-1) q after the LA stages
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
       double r = pol.mulmod(__longlong_as_double(x[i]), exd);  // x N^-1 R^-1, |r| < 1.1 q
       r = r < 0.0 ? __dadd_rn(r, pol.q) : r;
       r = r >= pol.q ? __dadd_rn(r, -pol.q) : r;
-      d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = tb::FastF64Pol::to_int(r);
+      d[(unsigned)tb::tile_x(tr, i, f0) << LB] = tb::FastF64Pol::to_int(r);
     }
     return;
   }
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const u64 y = tb::shoup((u64)x[i], P.ex, P.ex_s, P.q);
-    d[(unsigned)tb::tile_x(tr, i, f0) << c.LB] = (i64)(y >= P.q ? y - P.q : y);
+    d[(unsigned)tb::tile_x(tr, i, f0) << LB] = (i64)(y >= P.q ? y - P.q : y);
   }
 }
 
