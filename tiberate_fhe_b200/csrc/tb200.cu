@@ -773,8 +773,22 @@ static int launch_fast_inv_A(const tb200_ctx* c, TbView src, TbView dst, int row
   }
   return 0;
 }
-static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
-                         tb200_stream st) {
+// leading rows of [prime0, prime0 + rows) that take the FP64 butterflies, provided no later row does
+// (prime order is [40-bit scale primes..., base, special...], so with every small prime on the FP64
+// pipe this is the whole scale-prime prefix); 0 when the FP64 rows are scattered
+static int f64_prefix(const tb200_ctx* c, int prime0, int rows) {
+  int nf = 0;
+  while (nf < rows && c->fps[prime0 + nf].f64) ++nf;
+  for (int r = nf; r < rows; ++r)
+    if (c->fps[prime0 + r].f64) return 0;
+  return nf;
+}
+static TbView rows_from(TbView v, int r) {
+  v.p += (long)r * v.rs;
+  return v;
+}
+static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, TbView src, TbView dst, int rows,
+                              int batch, int prime0, tb200_stream st) {
   const int te = c->N < TB_TILE ? c->N : TB_TILE;
   // A CTA can walk over `bper` batch entries of one (limb, tile) to keep its twiddles in L1.  Measured
   // on B200 (logN16, chunk 16): bper = 8..16 is 12 % SLOWER than one entry per CTA at 2 or 3 CTAs/SM
@@ -782,23 +796,34 @@ static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView ds
   const int bper = 1;
   const int gz = (batch + bper - 1) / bper;
   const dim3 grid((unsigned)(c->N / te), (unsigned)rows, (unsigned)gz), block((unsigned)(te / 16));
-  switch (c->LB) {
-#define BCASE(n)                                                                                 \
-  case n: {                                                                                      \
+  switch (c->LB * 2 + (f64only ? 1 : 0)) {
+#define BCASE(n, F)                                                                              \
+  case n * 2 + (F ? 1 : 0): {                                                                    \
     if (inverse) {                                                                               \
-      auto kfn = k_fast_inv_B<n>;                                                                \
+      auto kfn = k_fast_inv_B<n, F>;                                                             \
       LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
     } else {                                                                                     \
-      auto kfn = k_fast_fwd_B<n>;                                                                \
+      auto kfn = k_fast_fwd_B<n, F>;                                                             \
       LAUNCHN("k_fast_fwd_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
     }                                                                                            \
   } break;
-    BCASE(4) BCASE(5) BCASE(6) BCASE(7) BCASE(8)
+    BCASE(4, false) BCASE(5, false) BCASE(6, false) BCASE(7, false) BCASE(8, false)
+    BCASE(4, true) BCASE(5, true) BCASE(6, true) BCASE(7, true) BCASE(8, true)
 #undef BCASE
     default:
       return fail(TB200_EINVAL, "unsupported LB %d", c->LB);
   }
   return 0;
+}
+// FP64 rows and integer rows go to separate launches: the FP64-only kernels need 64 registers (4 CTAs per SM)
+static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
+                         tb200_stream st) {
+  const int nf = f64_prefix(c, prime0, rows);
+  int rc = 0;
+  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st))) return rc;
+  if (nf < rows)
+    rc = launch_fast_B_rows(c, inverse, false, rows_from(src, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st);
+  return rc;
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
 static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,

@@ -221,9 +221,14 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
 // forward pass B; outputs: small primes < 72q, other primes reduced to [0, 2q).
 // A CTA owns one (limb, 4096-residue tile) and can walk over `bper` consecutive batch entries (the
 // launcher uses bper = 1: see launch_fast_B for the measurement).
-template <int LB>
-__global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst, int prime0, int batch,
-                                                       int bper) {
+#ifndef TB_F64_MINB
+#define TB_F64_MINB 4
+#endif
+// F64ONLY: every limb row of the launch takes the FP64 butterflies (the launcher splits the rows); without
+// the integer policies the kernel fits 64 registers and a fourth CTA per SM.
+template <int LB, bool F64ONLY>
+__global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst,
+                                                                               int prime0, int batch, int bper) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -242,16 +247,18 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, 
     // round-0 layout: 16 consecutive threads read 16 consecutive residues (one 128-byte line)
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
-    if (P.f64) {
+    if (F64ONLY || P.f64) {
       const tb::FastF64Pol pol{P.qd, P.qinv};
       tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.twd + ((long)g << c.logN), pol, slot);  // doubles from pass A
       tile_f64_reduce<true>(x, pol);  // [0, q)
-    } else if (P.small) {
-      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-    } else {
-      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+    } else if constexpr (!F64ONLY) {
+      if (P.small) {
+        tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+      } else {
+        tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
+        for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
+      }
     }
     // final layout (field 0): a thread owns 16 consecutive residues.  Storing them directly would make
     // every warp instruction touch 32 different 128-byte lines (ncu: the L1TEX data pipe was 79 % busy),
@@ -273,9 +280,9 @@ __global__ void __launch_bounds__(256, 3) k_fast_fwd_B(TbDevFast c, TbView src, 
 }
 
 // inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
-template <int LB>
-__global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst, int prime0, int batch,
-                                                       int bper) {
+template <int LB, bool F64ONLY>
+__global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst,
+                                                                               int prime0, int batch, int bper) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -304,15 +311,16 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_B(TbDevFast c, TbView src, 
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
-    if (P.f64) {  // inputs in [0, 4q): after the LB stages < 2^(LB+2) q < 2^52; renormalised before the store
+    if (F64ONLY || P.f64) {  // inputs in [0, 4q): after the LB stages < 2^(LB+2) q < 2^52; renormalised before the store
       const tb::FastF64Pol pol{P.qd, P.qinv};
       tile_to_f64(x);
       tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, c.itwd + ((long)g << c.logN), pol, slot);
       tile_f64_reduce<false>(x, pol);  // stays double for pass A'
-    } else if (P.small) {
-      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-    } else {
-      tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+    } else if constexpr (!F64ONLY) {
+      if (P.small)
+        tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+      else
+        tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = x[i];
