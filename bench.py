@@ -136,7 +136,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 (exact; 40-bit-prime butterflies as error-free FP64 products)", "data": "synthetic",
         "config": {"workload": "logN16 preset, level 0, cc_mult(pre_rescale)+relinearize, 1 ciphertext pair per step",
                    "note": "the reference has no CPU path (GPU-only); this arm times the CPU oracle port of its "
                            "algorithm on the host cores (NumPy + C/OpenMP)"},
@@ -276,8 +276,8 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": tms / nl, "launches_per_step": nl // psteps,
-                "note": "algorithmic limb passes of this kernel class per HMult x N x 8 B (DESIGN.md 4); the kernel is "
-                        "bound by the integer pipes (ncu: math_pipe_throttle), not by HBM"}
+                "note": "algorithmic limb passes of this kernel class per HMult x N x 8 B (DESIGN.md 4); ncu: FP64 pipe "
+                        "39 %, ALU 44 %, issue slots 58 % busy -- co-limited by instruction issue and HBM, see DESIGN.md 6"}
     elif top is not None:
         nl, tms = kern[top]
         roof = {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
@@ -380,7 +380,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "int64 (exact; 40-bit-prime butterflies as error-free FP64 products)", "data": "synthetic",
             "config": {"workload": "logN16 preset (N=65536, 35 ordinary + 4 special primes, 10 digit groups), level 0, "
                                    "cc_mult(pre_rescale)+relinearize", "batch_per_gpu": B, "chunk": args.chunk,
                        "sharding": "ciphertext batch, no data-path collective",

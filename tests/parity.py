@@ -226,6 +226,15 @@ def check_ntt(s: Setup, level=0, with_special=True, batch=2):
     u = h.dev(neg)
     ctx.ntt(u, pr[0], False)
     eq(h, u, eng.ntt(neg, pr), "ntt_radix2 on negative lazy input")
+    # unreduced sums of lazy values on the 40-bit limbs (documented domain of the mod-q route: |x| < 2^51)
+    wide = want[0].copy()
+    for r, g in enumerate(pr):
+        if o.q[g] < (1 << 42):
+            wide[r, 0:N:7] += 300 * o.q[g]
+            wide[r, 3:N:11] -= 411 * o.q[g]
+    u = h.dev(wide)
+    ctx.intt(u, pr[0], 2)
+    eq(h, u, eng.intt(wide, pr, 2), "intt_radix2_exit_reduce on unreduced lazy input")
     # row-offset view (the reference's rescale outputs are views with storage offset N)
     big = h.dev(np.concatenate([a[0][:1], a[0]], axis=0))
     view = big[1:]

@@ -720,6 +720,8 @@ extern "C" int tb200_ntt(tb200_ctx* c, int rows, int batch, int prime0, const tb
   POST();
   return 0;
 }
+static int fast_inverse_exit(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
+                             tb200_stream st, int mac_chain = 0, bool wide_in = false);
 extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const tb200_poly* a, int mode,
                           tb200_stream st) {
   if (!c) return fail(TB200_EINVAL, "null context");
@@ -727,7 +729,11 @@ extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const t
   CHECK_POLY(a);
   if (batch < 1 || mode < 0 || mode > 3) return fail(TB200_EINVAL, "bad batch/mode");
   CK(cudaSetDevice(c->device));
-  int rc = ntt_inverse(c, view(a), view(a), rows, batch, prime0, mode, st);
+  // intt_radix2_exit_reduce returns canonical residues, so the mod-q transforms give the same bits
+  // (domain: |x| < 2^51 on the FP64 limbs, (-2q, 2q) elsewhere -- every lazy value the ops produce;
+  // tb200_ctx_set_fast(ctx, 0) selects the reference's own butterflies for anything wider)
+  int rc = (c->fast && mode == 2) ? fast_inverse_exit(c, view(a), view(a), rows, batch, prime0, st, 0, true)
+                                  : ntt_inverse(c, view(a), view(a), rows, batch, prime0, mode, st);
   if (rc) return rc;
   POST();
   return 0;
@@ -788,7 +794,7 @@ static TbView rows_from(TbView v, int r) {
   return v;
 }
 static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, TbView src, TbView dst, int rows,
-                              int batch, int prime0, tb200_stream st) {
+                              int batch, int prime0, tb200_stream st, bool wide_in = false) {
   const int te = c->N < TB_TILE ? c->N : TB_TILE;
   // A CTA can walk over `bper` batch entries of one (limb, tile) to keep its twiddles in L1.  Measured
   // on B200 (logN16, chunk 16): bper = 8..16 is 12 % SLOWER than one entry per CTA at 2 or 3 CTAs/SM
@@ -799,8 +805,11 @@ static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, Tb
   switch (c->LB * 2 + (f64only ? 1 : 0)) {
 #define BCASE(n, F)                                                                              \
   case n * 2 + (F ? 1 : 0): {                                                                    \
-    if (inverse) {                                                                               \
-      auto kfn = k_fast_inv_B<n, F>;                                                             \
+    if (inverse && wide_in) {                                                                    \
+      auto kfn = k_fast_inv_B<n, F, true>;                                                       \
+      LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
+    } else if (inverse) {                                                                        \
+      auto kfn = k_fast_inv_B<n, F, false>;                                                      \
       LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
     } else {                                                                                     \
       auto kfn = k_fast_fwd_B<n, F>;                                                             \
@@ -817,12 +826,13 @@ static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, Tb
 }
 // FP64 rows and integer rows go to separate launches: the FP64-only kernels need 64 registers (4 CTAs per SM)
 static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
-                         tb200_stream st) {
+                         tb200_stream st, bool wide_in = false) {
   const int nf = f64_prefix(c, prime0, rows);
   int rc = 0;
-  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st))) return rc;
+  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st, wide_in))) return rc;
   if (nf < rows)
-    rc = launch_fast_B_rows(c, inverse, false, rows_from(src, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st);
+    rc = launch_fast_B_rows(c, inverse, false, rows_from(src, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st,
+                            wide_in);
   return rc;
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
@@ -848,8 +858,8 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
 // mac_chain: the input is the key inner product of an FP64-extended digit expansion, whose FP64 limbs
 // carry no Montgomery factor (extend_prologue_f64): their exit multiplies by N^-1 instead of N^-1 R^-1
 static int fast_inverse_exit(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
-                             tb200_stream st, int mac_chain = 0) {
-  int rc = launch_fast_B(c, true, src, dst, rows, batch, prime0, st);
+                             tb200_stream st, int mac_chain, bool wide_in) {
+  int rc = launch_fast_B(c, true, src, dst, rows, batch, prime0, st, wide_in);
   if (rc) return rc;
   return launch_fast_inv_A(c, dst, dst, rows, batch, prime0, mac_chain, st);
 }

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(T
 }
 
 // inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
-template <int LB, bool F64ONLY>
+// WIDE_IN (the exposed tb200_intt): FP64 limbs accept any |x| < 2^51 and are reduced first.
+template <int LB, bool F64ONLY, bool WIDE_IN>
 __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst,
                                                                                int prime0, int batch, int bper) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
@@ -305,8 +306,13 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(T
     for (int i = 0; i < 8; ++i) {
       const longlong2 v = sv[i * nt + tid];
       const int e = 2 * (i * nt + tid);
-      sm[tb::pad16(e)] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
-      sm[tb::pad16(e + 1)] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
+      if (WIDE_IN && (F64ONLY || P.f64)) {
+        sm[tb::pad16(e)] = v.x;
+        sm[tb::pad16(e + 1)] = v.y;
+      } else {
+        sm[tb::pad16(e)] = v.x < 0 ? v.x + (i64)P.q2 : v.x;
+        sm[tb::pad16(e + 1)] = v.y < 0 ? v.y + (i64)P.q2 : v.y;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -314,6 +320,7 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(T
     if (F64ONLY || P.f64) {  // inputs in [0, 4q): after the LB stages < 2^(LB+2) q < 2^52; renormalised before the store
       const tb::FastF64Pol pol{P.qd, P.qinv};
       tile_to_f64(x);
+      if constexpr (WIDE_IN) tile_f64_reduce<false>(x, pol);
       tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, c.itwd + ((long)g << c.logN), pol, slot);
       tile_f64_reduce<false>(x, pol);  // stays double for pass A'
     } else if constexpr (!F64ONLY) {
