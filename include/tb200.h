@@ -198,6 +198,31 @@ int tb200_cc_addsub(tb200_ctx*, int level, int batch, int sub, const tb200_poly*
                     const tb200_poly* b0, const tb200_poly* b1, const tb200_poly* out0, const tb200_poly* out1,
                     tb200_stream);
 
+/* ---- CSPRNG operators (torch namespace tiberate_csprng_ops) ----------------------
+ * State rows: 16 int64 per ChaCha20 block, one 32-bit word each -- constants, key, 64-bit counter in
+ * words 12-13, nonce (tiberate/rng/csprng/csprng.py:113-178).  All buffers are device pointers of
+ * contiguous int64 on `device`; q / lut are HOST pointers (the reference passes numpy addresses,
+ * csprng.py:249-252, discrete_gaussian_sampler.py:104-106) of at most 128 words. */
+/* chacha20 (csrc/csprng/chacha20.cpp:11-32): out[n][16] = blocks of the current states; every row's
+ * counter then advances by `step`. */
+int tb200_chacha20(int device, int64_t* states, int64_t n_rows, int64_t* out, int64_t step, tb200_stream);
+/* randint_fast (randint.cpp:23-35, cuda/randint_cuda.cu:23-87): states [channels][L][16] ->
+ * out [channels][4L] = floor(X * q[c] / 2^128) + shift from 128 random bits each; states stepped. */
+int tb200_randint_fast(int device, int64_t* states, int channels, int64_t L, const uint64_t* q_host,
+                       int64_t shift, int64_t step, int64_t* out, tb200_stream);
+/* discrete_gaussian_fast (discrete_gaussian.cpp, cuda/discrete_gaussian_cuda.cu:19-101): states [n][16]
+ * -> out [4n]; lut_host = lows[size] then highs[size] of the CDT binary search tree. */
+int tb200_discrete_gaussian_fast(int device, int64_t* states, int64_t n_rows, const uint64_t* lut_host, int size,
+                                 int depth, int64_t step, int64_t* out, tb200_stream);
+/* randint / discrete_gaussian (the two-step variants): in place on random words [channels][L][16] /
+ * [n][16]; the sample of words 4j..4j+3 replaces word 4j. */
+int tb200_randint(int device, int64_t* words, int channels, int64_t L, const uint64_t* q_host, tb200_stream);
+int tb200_discrete_gaussian(int device, int64_t* words, int64_t n_rows, const uint64_t* lut_host, int size, int depth,
+                            tb200_stream);
+/* randround (randround.cpp:10-19, cuda/randround_cuda.cu:4-36): words[i] <- sign(c_i) * (floor|c_i| +
+ * [words[i] < rn(frac(|c_i|) * 2^32)]), words[i] a 32-bit random word. */
+int tb200_randround(int device, const double* coef, int64_t* words, int64_t n, tb200_stream);
+
 /* number of kernel launches issued by this library since process start (bench.py gpu_launches) */
 int64_t tb200_launch_count(void);
 /* per-kernel timing for bench.py's roofline: while enabled every launch is bracketed by CUDA events;

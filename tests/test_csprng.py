@@ -1,0 +1,94 @@
+"""CSPRNG operators: oracle pins (RFC 8439 known answer, the reference's CDT tree),
+the kernels compiled for the host against the oracle (CPU), the CUDA kernels against the oracle and
+the Csprng class against the oracle's restatement of the reference class (GPU)."""
+
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import csprng_checks as cc  # noqa: I001
+from oracle import csprng as oc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def test_oracle_rfc8439_block_known_answer():
+    st = cc.make_states(1, cc.KEY, [0x4A000000, 0])
+    st[0, 12], st[0, 13] = 1, 0x09000000
+    out = oc.chacha20_block(st)[0]
+    assert [hex(v) for v in out[:4]] == ["0xe4e7f110", "0x15593bd1", "0x1fdd0f50", "0xc47120a3"]
+    assert [hex(v) for v in out[12:]] == ["0xd19c12b5", "0xb94e16de", "0xe883d0cb", "0x4e3c50a2"]
+
+
+def test_oracle_cdt_tree_matches_reference_fixture():
+    """tests/golden/ref_cdt_sigma3.2.json was produced by the reference's own
+    build_CDT_binary_search_tree (tests/golden/make_ref_golden_csprng.py)."""
+    with open(os.path.join(HERE, "golden", "ref_cdt_sigma3.2.json")) as f:
+        g = json.load(f)
+    lut, size, depth = oc.build_cdt_tree()
+    assert (size, depth) == (g["size"], g["depth"])
+    assert [int(v) for v in lut] == [int(v) for v in g["lut"]]
+    from tiberate_fhe_b200.rng.csprng import build_cdt_tree
+
+    lut2, s2, d2 = build_cdt_tree()
+    assert (s2, d2) == (size, depth) and np.array_equal(lut2, lut)
+
+
+def test_oracle_randint_is_the_reference_carry_chain():
+    """randint_cuda.cu:56-81 computes floor(X p / 2^128) with an explicit 32-bit carry chain; restate
+    that chain literally and compare with the big-integer floor on edge values."""
+    M = 0xFFFFFFFF
+    rng = np.random.default_rng(1)
+    cases = [(0, 0, 0, 0, 3), (M, M, M, M, (1 << 64) - 1), (M, M, M, M, 3), (1, 0, 0, 0, (1 << 63))]
+    for _ in range(300):
+        w = [int(v) for v in rng.integers(0, 1 << 32, 4)]
+        cases.append((*w, int(rng.integers(2, 1 << 62))))
+    for x0, x1, x2, x3, p in cases:
+        x_low = (x0 << 32) | x1
+        alpha = (p * x_low) >> 64
+        pl, ph, xhh, xhl = p & M, p >> 32, x2, x3
+        plxhl, plxhh, phxhl, phxhh = pl * xhl, pl * xhh, ph * xhl, ph * xhh
+        carry = ((plxhl & M) + (alpha & M)) >> 32
+        carry = (carry + (plxhl >> 32) + (alpha >> 32) + (phxhl & M) + (plxhh & M)) >> 32
+        sample = (carry + (phxhl >> 32) + (plxhh >> 32) + phxhh) & ((1 << 64) - 1)
+        X = (((x2 << 32) | x3) << 64) | x_low
+        assert sample == (X * p) >> 128
+
+
+@pytest.mark.parametrize("check", cc.ALL, ids=lambda f: f.__name__)
+def test_emulated_kernels(emu_lib, check):
+    check(emu_lib, cc.Buf(False))
+
+
+def test_oracle_csprng_golden():
+    """The oracle's Csprng restatement against outputs of the reference's Csprng + CUDA extension
+    (fixture generated on a B200 by tests/golden/make_ref_golden_csprng.py)."""
+    path = os.path.join(HERE, "golden", "ref_csprng.json")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated yet")
+    import golden_csprng
+
+    golden_csprng.check_against(path, golden_csprng.run_oracle)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("check", cc.ALL, ids=lambda f: f.__name__)
+def test_gpu_kernels(check):
+    from tiberate_fhe_b200._native import get_lib
+
+    check(get_lib(), cc.Buf(True))
+
+
+@pytest.mark.gpu
+def test_gpu_csprng_class_matches_oracle_and_golden():
+    import golden_csprng
+
+    path = os.path.join(HERE, "golden", "ref_csprng.json")
+    ours = golden_csprng.run_tb200()
+    assert ours == golden_csprng.run_oracle(), "Csprng (libtb200) vs the oracle's restatement"
+    if os.path.exists(path):
+        golden_csprng.check_against(path, lambda: ours)

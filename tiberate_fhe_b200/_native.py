@@ -73,6 +73,12 @@ SIGNATURES = {
     "tb200_switch_key": (_i, [_vp, _i, _i, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),
     "tb200_pc_mult": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_addsub": (_i, [_vp, _i, _i, _i, PP, PP, PP, PP, PP, PP, _vp]),
+    "tb200_chacha20": (_i, [_i, C.c_void_p, _i64, C.c_void_p, _i64, C.c_void_p]),
+    "tb200_randint_fast": (_i, [_i, C.c_void_p, _i, _i64, C.c_void_p, _i64, _i64, C.c_void_p, C.c_void_p]),
+    "tb200_discrete_gaussian_fast": (_i, [_i, C.c_void_p, _i64, C.c_void_p, _i, _i, _i64, C.c_void_p, C.c_void_p]),
+    "tb200_randint": (_i, [_i, C.c_void_p, _i, _i64, C.c_void_p, C.c_void_p]),
+    "tb200_discrete_gaussian": (_i, [_i, C.c_void_p, _i64, C.c_void_p, _i, _i, C.c_void_p]),
+    "tb200_randround": (_i, [_i, C.c_void_p, C.c_void_p, _i64, C.c_void_p]),
     "tb200_launch_count": (_i64, []),
     "tb200_prof_enable": (None, [_i]),
     "tb200_prof_collect": (_i, [C.c_char_p, _i]),

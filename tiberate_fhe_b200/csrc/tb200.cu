@@ -6,6 +6,7 @@
 
 #include "../../include/tb200.h"
 #include "tb200_ctx.h"
+#include "tb200_csprng.cuh"
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -1453,6 +1454,82 @@ extern "C" int tb200_cc_addsub(tb200_ctx* c, int level, int batch, int sub, cons
     else
       launch_pw<3>(c, g, L, batch, st);
   }
+  POST();
+  return 0;
+}
+
+// ---- CSPRNG operators ---------------------------------------------------------------------------------
+static int rng_table(TbRngTable* t, const uint64_t* host, int n, const char* what) {
+  if (!host || n < 1 || n > TB_RNG_MAXQ) return fail(TB200_EINVAL, "%s: table must hold 1..%d words", what, TB_RNG_MAXQ);
+  memset(t, 0, sizeof(*t));
+  for (int i = 0; i < n; ++i) t->v[i] = host[i];
+  return 0;
+}
+#define RNG_ENTER(ptr, cnt, what)                                                                 \
+  if (!(ptr) || (cnt) < 1) return fail(TB200_EINVAL, what ": null buffer or empty");               \
+  if (((uintptr_t)(ptr)&15) != 0) return fail(TB200_EINVAL, what ": buffers must be 16-byte aligned"); \
+  CK(cudaSetDevice(device));
+
+extern "C" int tb200_chacha20(int device, int64_t* states, int64_t n_rows, int64_t* out, int64_t step, tb200_stream st) {
+  RNG_ENTER(states, n_rows, "chacha20");
+  if (!out || ((uintptr_t)out & 15) != 0) return fail(TB200_EINVAL, "chacha20: bad output buffer");
+  LAUNCH(k_rng_chacha20, dim3((unsigned)((n_rows + 127) / 128)), dim3(128), st, (i64*)states, (i64*)out, (long)n_rows,
+         (i64)step);
+  POST();
+  return 0;
+}
+extern "C" int tb200_randint_fast(int device, int64_t* states, int channels, int64_t L, const uint64_t* q_host,
+                                  int64_t shift, int64_t step, int64_t* out, tb200_stream st) {
+  RNG_ENTER(states, L, "randint_fast");
+  if (!out || ((uintptr_t)out & 15) != 0) return fail(TB200_EINVAL, "randint_fast: bad output buffer");
+  TbRngTable q;
+  int rc = rng_table(&q, q_host, channels, "randint_fast");
+  if (rc) return rc;
+  LAUNCH(k_rng_randint_fast, dim3((unsigned)((L + 127) / 128), (unsigned)channels), dim3(128), st, (i64*)states,
+         (i64*)out, (long)L, q, (i64)shift, (i64)step);
+  POST();
+  return 0;
+}
+extern "C" int tb200_discrete_gaussian_fast(int device, int64_t* states, int64_t n_rows, const uint64_t* lut_host,
+                                            int size, int depth, int64_t step, int64_t* out, tb200_stream st) {
+  RNG_ENTER(states, n_rows, "discrete_gaussian_fast");
+  if (!out || ((uintptr_t)out & 15) != 0) return fail(TB200_EINVAL, "discrete_gaussian_fast: bad output buffer");
+  if (depth < 1 || depth > 6 || size != (1 << depth) - 1) return fail(TB200_EINVAL, "discrete_gaussian_fast: bad tree");
+  TbRngTable lut;
+  int rc = rng_table(&lut, lut_host, 2 * size, "discrete_gaussian_fast");
+  if (rc) return rc;
+  LAUNCH(k_rng_gaussian_fast, dim3((unsigned)((n_rows + 127) / 128)), dim3(128), st, (i64*)states, (i64*)out,
+         (long)n_rows, lut, size, depth, (i64)step);
+  POST();
+  return 0;
+}
+extern "C" int tb200_randint(int device, int64_t* words, int channels, int64_t L, const uint64_t* q_host,
+                             tb200_stream st) {
+  RNG_ENTER(words, L, "randint");
+  TbRngTable q;
+  int rc = rng_table(&q, q_host, channels, "randint");
+  if (rc) return rc;
+  LAUNCH(k_rng_randint_inplace, dim3((unsigned)((L + 127) / 128), (unsigned)channels), dim3(128), st, (i64*)words, (long)L,
+         q);
+  POST();
+  return 0;
+}
+extern "C" int tb200_discrete_gaussian(int device, int64_t* words, int64_t n_rows, const uint64_t* lut_host, int size,
+                                       int depth, tb200_stream st) {
+  RNG_ENTER(words, n_rows, "discrete_gaussian");
+  if (depth < 1 || depth > 6 || size != (1 << depth) - 1) return fail(TB200_EINVAL, "discrete_gaussian: bad tree");
+  TbRngTable lut;
+  int rc = rng_table(&lut, lut_host, 2 * size, "discrete_gaussian");
+  if (rc) return rc;
+  LAUNCH(k_rng_gaussian_inplace, dim3((unsigned)((n_rows + 127) / 128)), dim3(128), st, (i64*)words, (long)n_rows, lut,
+         size, depth);
+  POST();
+  return 0;
+}
+extern "C" int tb200_randround(int device, const double* coef, int64_t* words, int64_t n, tb200_stream st) {
+  if (!coef || !words || n < 1) return fail(TB200_EINVAL, "randround: null buffer or empty");
+  CK(cudaSetDevice(device));
+  LAUNCH(k_rng_randround, dim3((unsigned)((n + 255) / 256)), dim3(256), st, coef, (i64*)words, (long)n);
   POST();
   return 0;
 }

@@ -32,4 +32,4 @@ def context_for(t) -> Tb200Context:
         ) from None
 
 
-from . import he_ops, mont_ops, ntt2_ops  # noqa: E402,F401
+from . import csprng_ops, he_ops, mont_ops, ntt2_ops  # noqa: E402,F401
