@@ -13,7 +13,8 @@ Differences, all deliberate:
     keys is processed by one call (BASELINE.json configs[2]);
   * single device per engine: limb sharding across devices (reference `devices=[...]`) is replaced
     by batch sharding across ranks (tiberate_fhe_b200/dist.py).
-Key generation, encryption, decryption and encoding are outside the hot path.
+Key generation, encryption and decryption live in keygen.py, the CSPRNG (8f-1) in
+rng/csprng.py; `seed` (8 words) / `nonce` (2 words) fix the CSPRNG stream, None draws from os.urandom.
 """
 
 from __future__ import annotations
@@ -22,6 +23,7 @@ import torch
 
 from . import wrapper
 from .context import KeySwitchKeyView, Tb200Context, galois_element
+from .keygen import KeyGenMixin
 from .presets import PRESETS
 from .typing import FLAGS, Ciphertext, CiphertextTriplet, KeySwitchKey, Plaintext
 
@@ -43,8 +45,8 @@ class MontgomeryStateError(Exception):
         super().__init__(f"Montgomery state mismatch: expected MONTGOMERY_STATE={expected}")
 
 
-class CkksEngine:
-    def __init__(self, ckks_config=None, devices=None, *, chunk: int = 4):
+class CkksEngine(KeyGenMixin):
+    def __init__(self, ckks_config=None, devices=None, *, chunk: int = 4, seed=None, nonce=None):
         """ckks_config: None (reference default: logN15 preset), an int logN naming a preset, or a dict
         with keys logN, q (prime chain [scale..., base, special...]), num_special_primes[, scale_bits]."""
         if ckks_config is None:
@@ -64,6 +66,7 @@ class CkksEngine:
         self.logN, self.N = self.ctx.logN, self.ctx.N
         self.num_special_primes = self.ctx.K
         self._keys = {}
+        self._init_keygen(seed, nonce)  # CSPRNG + key-generation constants (keygen.py)
 
     @property
     def num_levels(self) -> int:  # ckks_engine.py:102-104
@@ -117,6 +120,7 @@ class CkksEngine:
 
     # ---- multiplication ------------------------------------------------------------------------
     def cc_mult(self, a: Ciphertext, b: Ciphertext, evk=None, *, pre_rescale=True, post_relin=True):
+        evk = evk or (self.evk if post_relin else None)
         level = a.level
         if pre_rescale and level + 1 >= self.num_levels:
             raise MaximumLevelError(level=level, level_max=self.num_levels)
@@ -134,6 +138,7 @@ class CkksEngine:
                                  level=lvl, misc=dict(a.misc))
 
     def relinearize(self, ct_triplet: CiphertextTriplet, evk=None) -> Ciphertext:
+        evk = evk or self.evk
         if not ct_triplet.has_flag(FLAGS.NTT_STATE):
             raise NTTStateError(expected=True)
         if not ct_triplet.has_flag(FLAGS.MONTGOMERY_STATE):
