@@ -92,3 +92,33 @@ def test_gpu_csprng_class_matches_oracle_and_golden():
     assert ours == golden_csprng.run_oracle(), "Csprng (libtb200) vs the oracle's restatement"
     if os.path.exists(path):
         golden_csprng.check_against(path, lambda: ours)
+
+
+def test_codec_permutations_and_encode_match_reference_fixture():
+    """the slot permutations depend on the reference's cycle enumeration; fixture from the
+    reference's own prepost_perms (tests/golden/make_ref_golden_csprng.py codec)."""
+    import hashlib
+
+    import torch
+
+    from tiberate_fhe_b200 import codec
+
+    with open(os.path.join(HERE, "golden", "ref_codec.json")) as f:
+        g = json.load(f)
+    for logN, (hpre, hpost) in g["perms"].items():
+        pre, post = codec.prepost_perms(1 << int(logN), "cpu")
+        assert hashlib.sha256(pre.numpy().astype(np.int64).tobytes()).hexdigest() == hpre, f"pre_perm logN{logN}"
+        assert hashlib.sha256(post.numpy().astype(np.int64).tobytes()).hexdigest() == hpost, f"post_perm logN{logN}"
+    N = 1 << 10
+    gen = torch.Generator().manual_seed(3)
+    m = torch.randn(N // 2, generator=gen, dtype=torch.float64) + 1j * torch.randn(N // 2, generator=gen,
+                                                                                  dtype=torch.float64)
+    enc = codec.encode(m, device="cpu", deviation=1.25, return_without_scaling=True)
+    assert np.allclose(enc[:8].numpy(), g["encode_logN10"], rtol=1e-12, atol=1e-12)
+    # decode(encode(m)) = m  (canonical embedding round trip, no scaling)
+    class _Cpu:  # decode() derives the device name from the tensor; CPU tensors have no index
+        pass
+    dec = torch.fft.ifft(enc * codec._twister(N, "cpu", +1), norm="forward")
+    back = torch.zeros_like(dec)
+    back[codec.prepost_perms(N, "cpu")[1]] = dec
+    assert torch.allclose(back[: N // 2], m * 1.25, atol=1e-9)

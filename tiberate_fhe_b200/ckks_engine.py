@@ -23,7 +23,7 @@ import torch
 
 from . import wrapper
 from .context import KeySwitchKeyView, Tb200Context, galois_element
-from .keygen import KeyGenMixin
+from .keygen import CodecMixin, KeyGenMixin
 from .presets import PRESETS
 from .typing import FLAGS, Ciphertext, CiphertextTriplet, KeySwitchKey, Plaintext
 
@@ -45,8 +45,9 @@ class MontgomeryStateError(Exception):
         super().__init__(f"Montgomery state mismatch: expected MONTGOMERY_STATE={expected}")
 
 
-class CkksEngine(KeyGenMixin):
-    def __init__(self, ckks_config=None, devices=None, *, chunk: int = 4, seed=None, nonce=None):
+class CkksEngine(KeyGenMixin, CodecMixin):
+    def __init__(self, ckks_config=None, devices=None, *, chunk: int = 4, seed=None, nonce=None, bias_guard=True,
+                 norm="forward"):
         """ckks_config: None (reference default: logN15 preset), an int logN naming a preset, or a dict
         with keys logN, q (prime chain [scale..., base, special...]), num_special_primes[, scale_bits]."""
         if ckks_config is None:
@@ -67,6 +68,7 @@ class CkksEngine(KeyGenMixin):
         self.num_special_primes = self.ctx.K
         self._keys = {}
         self._init_keygen(seed, nonce)  # CSPRNG + key-generation constants (keygen.py)
+        self._init_codec(bias_guard, norm)
 
     @property
     def num_levels(self) -> int:  # ckks_engine.py:102-104
@@ -201,7 +203,9 @@ class CkksEngine(KeyGenMixin):
         level = ct.level
         cache = pt.cache[level]
         if "pc_mult" not in cache:
-            raise KeyError("plaintext has no NTT-form cache for this level; encoding is outside the hot path")
+            if getattr(pt, "src", None) is None:
+                raise KeyError("plaintext has neither a message nor an NTT-form cache for this level")
+            self._plain_operand(pt, level, "pc_mult")  # encode -> tile_unsigned -> enter_ntt_radix2
         if post_rescale and level + 1 >= self.num_levels:
             raise MaximumLevelError(level=level, level_max=self.num_levels)
         c0, c1 = self._t(ct.data[0]), self._t(ct.data[1])

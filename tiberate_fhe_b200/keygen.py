@@ -272,3 +272,170 @@ class KeyGenMixin:
         ntt2_ops.ntt_radix2(s, None, None, None, self.ctx.K)
         sk_rot = SecretKey(data=s, flags=FLAGS.MONTGOMERY_STATE | FLAGS.NTT_STATE, level=0, logN=self.logN)
         return RotationKey.wrap(self.create_key_switching_key(sk_rot, sk, a=a), delta=delta)
+
+
+class CodecMixin:
+    """encode / decode / encodecrypt / decryptcode / pc_add: ckks_engine.py:258-291
+    (deviations, corrections), :437-479, :2178-2422, :2516-2539, with the reference's bias guard (the DC
+    coefficient's integral part travels as an exact RNS constant instead of through the float path)."""
+
+    def _init_codec(self, bias_guard=True, norm="forward"):
+        import numpy as np
+
+        ctx = self.ctx
+        self.bias_guard, self.norm = bias_guard, norm
+        self.scale = 2 ** ctx.scale_bits
+        self.alpha = [(self.scale / np.float64(q)) ** 2 for q in ctx.q[: ctx.num_scales]]
+        self.deviations = [1]
+        for al in self.alpha:
+            self.deviations.append(self.deviations[-1] ** 2 * al)
+        self.final_alpha = [self.scale / np.float64(ctx.q[l]) for l in range(ctx.num_scales)]
+        self.corrections = [1 / (d * fa) for d, fa in zip(self.deviations, self.final_alpha)]
+
+    def encode(self, m, level: int = 0, padding=True, scale=None):
+        from . import codec
+
+        if padding:
+            m = codec.padding(m, num_slots=self.num_slots)
+        return [codec.encode(m, scale=scale or self.scale, rng=self.rng, device=str(self.device),
+                             deviation=self.deviations[level], norm=self.norm)]
+
+    def decode(self, m, level=0, is_real: bool = False):
+        from . import codec
+
+        decoded = codec.decode(m[0].squeeze(), scale=self.scale, correction=self.corrections[level], norm=self.norm)
+        out = decoded[: self.N // 2].cpu().numpy()
+        return out.real if is_real else out
+
+    def encodecrypt(self, m, pk=None, *, level: int = 0, padding=True) -> Ciphertext:
+        import numpy as np
+
+        from . import codec
+
+        pk = pk or self.pk
+        if padding:
+            m = codec.padding(m=m, num_slots=self.num_slots)
+        pt = codec.encode(m, scale=self.scale, device=str(self.device), norm=self.norm, deviation=self.deviations[level],
+                          rng=self.rng, return_without_scaling=self.bias_guard)
+        mult_type = -2 if pk.has_flag(FLAGS.INCLUDE_SPECIAL) else -1
+        dc_rns = None
+        if self.bias_guard:
+            dc_integral = pt[0].item() // 1
+            pt[0] -= dc_integral
+            dc_scale = int(dc_integral) * int(self.scale)
+            dc_rns = torch.tensor([dc_scale % self.ctx.q[i] for i in self._primes(level, -1)], dtype=torch.int64,
+                                  device=self.device)
+            pt *= np.float64(self.scale)
+            pt = self.rng.randround(pt)
+        return self._encrypt_encoded([pt], pk, level, mult_type, dc_rns)
+
+    def _encrypt_encoded(self, encoded, pk, level, mult_type, dc_rns):
+        sp = self._sp(mult_type)
+        e0e1 = self.rng.discrete_gaussian(repeats=2)
+        e0, e1 = [e[0] for e in e0e1], [e[1] for e in e0e1]
+        e0_t = self._tile_unsigned(e0, level, mult_type)
+        e1_t = self._tile_unsigned(e1, level, mult_type)
+        pt_t = self._tile_unsigned(encoded, level, mult_type)
+        if dc_rns is not None:
+            pt_t[0][:, 0] += dc_rns
+        mont_ops.mont_enter_Rs_scale(pt_t, sp)
+        mont_ops.mont_reduce(pt_t, sp)
+        pte0 = mont_ops.mont_add(pt_t, e0_t, sp)
+        pk0, pk1 = [pk.data[0][0][level:]], [pk.data[1][0][level:]]
+        v = self.rng.randint(amax=2, shift=0, repeats=1)
+        v = self._tile_unsigned(v, level, mult_type)
+        self._enter_ntt(v, mult_type)
+        vpk0 = mont_ops.mont_mult(v, pk0, sp)
+        vpk1 = mont_ops.mont_mult(v, pk1, sp)
+        self._intt_exit(vpk0, mult_type)
+        self._intt_exit(vpk1, mult_type)
+        ct0 = mont_ops.mont_add_reduce_2q(vpk0, pte0, sp)
+        ct1 = mont_ops.mont_add_reduce_2q(vpk1, e1_t, sp)
+        return Ciphertext(data=[ct0, ct1], flags=(FLAGS.INCLUDE_SPECIAL if pk.has_flag(FLAGS.INCLUDE_SPECIAL)
+                                                   else FLAGS(0)), level=level, logN=self.logN)
+
+    def decryptcode(self, ct, sk=None, *, is_real=False, final_round=True):
+        from . import codec
+        from .typing import CiphertextTriplet
+
+        sk = sk or self.sk
+        level, K = ct.level, self.ctx.K
+        sk_data = sk.data[0][level:]
+        if isinstance(ct, CiphertextTriplet):
+            d0 = [ct.data[0][0].clone()]
+            ntt2_ops.intt_radix2_exit_reduce(d0, None, None, None, K)
+            d1_s = mont_ops.mont_mult([ct.data[1][0]], [sk_data], K)
+            s2 = mont_ops.mont_mult([sk_data], [sk_data], K)
+            d2_s2 = mont_ops.mont_mult([ct.data[2][0]], s2, K)
+            self._intt_exit(d1_s)
+            self._intt_exit(d2_s2)
+            pt = mont_ops.mont_add(d0, d1_s, K)
+            pt = mont_ops.mont_add(pt, d2_s2, K)
+            mont_ops.reduce_2q(pt, K)
+        else:
+            self._require_plain(ct)
+            a = ct.data[1][0].clone()
+            self._enter_ntt([a])
+            sa = mont_ops.mont_mult([a], [sk_data], K)
+            self._intt_exit(sa)
+            pt = mont_ops.mont_add([ct.data[0][0]], sa, K)
+            mont_ops.reduce_2q(pt, K)
+        include_special = ct.has_flag(FLAGS.INCLUDE_SPECIAL)
+        base_at = -K - 1 if include_special else -1
+        base = pt[0][base_at][None, :]
+        scaler = pt[0][0][None, :]
+        alive = self._primes(level, -1)
+        guard = len(alive) >= 3 and self.bias_guard
+        dc = 0
+        if guard:  # exact CRT of the DC coefficient over (base, first, second) primes (ckks_engine.py:2352-2383)
+            dc0, dc1, dc2 = base[0][0].item(), scaler[0][0].item(), pt[0][1][0].item()
+            base[0][0] = 0
+            scaler[0][0] = 0
+            q0 = self.base_prime
+            q1, q2 = self.ctx.q[alive[0]], self.ctx.q[alive[1]]
+            Q = q0 * q1 * q2
+            Q0, Q1, Q2 = q1 * q2, q0 * q2, q0 * q1
+            dc = (dc0 * pow(Q0, -1, q0) * Q0 + dc1 * pow(Q1, -1, q1) * Q1 + dc2 * pow(Q2, -1, q2) * Q2) % Q
+            dc = dc if dc <= Q // 2 else dc - Q
+            dc = (dc + (q1 - 1)) // q1
+        scaled = mont_ops.mont_sub([base], [scaler], K)
+        mont_ops.mont_enter_scalar(scaled, [self.final_scalar[level]], K)
+        mont_ops.reduce_2q(scaled, K)
+        mont_ops.make_signed(scaled, K)
+        if final_round:
+            rounding_prime = self.ctx.q[self.ctx.num_ordinary - 2]
+            scaled[0] += (scaler[0] > (rounding_prime // 2)) * 1
+        correction = self.corrections[level]
+        decoded = codec.decode(scaled[0][-1], scale=self.scale, correction=correction, norm=self.norm,
+                               return_without_scaling=self.bias_guard)
+        decoded = decoded[: self.N // 2].cpu().numpy()
+        # (as in the reference, the scaling is applied here -- a second time when bias_guard is off)
+        decoded = decoded / self.scale * correction
+        if guard:
+            decoded += dc / self.scale * correction
+        return decoded.real if is_real else decoded
+
+    # ---- plaintext operands (ckks_engine.py:2516-2560) ---------------------------------------------------
+    def _plain_operand(self, pt, level, kind):
+        cache = pt.cache[level]
+        if kind not in cache:
+            m = pt.src * math.sqrt(self.deviations[level + 1])
+            p = self.encode(m, level, scale=pt.scale)
+            p = self._tile_unsigned(p, level)
+            if kind == "pc_add":
+                mont_ops.mont_enter_Rs_scale(p, self.ctx.K)
+            else:
+                self._enter_ntt(p)
+            cache[kind] = p
+        return cache[kind]
+
+    def pc_add(self, pt, ct: Ciphertext, inplace: bool = False) -> Ciphertext:
+        from .wrapper import he_ops
+
+        p = self._plain_operand(pt, ct.level, "pc_add")
+        new_d0 = he_ops.pc_add_fused(ct.data[0], p, self.ctx.K)
+        if inplace:
+            ct.data[0] = new_d0
+            return ct
+        return Ciphertext(data=[new_d0, [d.clone() for d in ct.data[1]]], flags=ct._flags, level=ct.level,
+                          misc=dict(ct.misc))

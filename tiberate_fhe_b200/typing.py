@@ -79,8 +79,24 @@ class Plaintext(DataStruct):
     (tiberate/typing.py:318-409).  Encoding itself (float FFT) is outside the hot path: build one
     with `Plaintext.from_ntt(level, tensor)`."""
 
-    def __init__(self, data=None, *, flags=None, level: int = 0, **kwargs):
-        super().__init__(data, flags=flags, level=level, **kwargs)
+    def __init__(self, m=None, *, flags=None, level: int = 0, scale=None, **kwargs):
+        """m: the 1-D message (tensor / array / list / scalar) as in the reference's Plaintext(m), or None
+        when only a cache is supplied (from_ntt)."""
+        super().__init__(None, flags=flags, level=level, **kwargs)
+        if m is not None:
+            import numpy as np
+            import torch
+
+            if isinstance(m, np.ndarray):
+                m = torch.from_numpy(m)
+            elif isinstance(m, (int, float)):
+                m = torch.tensor([m])
+            elif not isinstance(m, torch.Tensor):
+                m = torch.tensor(m)
+            if m.dim() != 1:
+                raise RuntimeError(f"Plaintext source data must be 1D tensor, got {m.dim()}D tensor.")
+        self.src = m
+        self.scale = scale
         self.cache = defaultdict(dict)
 
     @classmethod
