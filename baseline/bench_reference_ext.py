@@ -75,6 +75,12 @@ def main():
         engine.nttCtx.intt_radix2_exit_reduce([x], 0)
 
     res["ntt_fwd_plus_inv_ms"] = timed(ntt_roundtrip)
+    # CSPRNG + self-contained engine path
+    q_all = engine.nttCtx.q_prepack[-2][0][0]
+    res["csprng_randint_allP_ms"] = timed(lambda: engine.rng.randint(q_all, repeats=engine.ckksCfg.num_special_primes))
+    res["csprng_gaussian2_ms"] = timed(lambda: engine.rng.discrete_gaussian(repeats=2))
+    res["encodecrypt_ms"] = timed(lambda: engine.encodecrypt(data))
+    res["decryptcode_ms"] = timed(lambda: engine.decryptcode(ct1))
     out = {
         "impl": "reference_cuda_ext", "logN": args.logN, "N": N, "limbs_level0": L,
         "iters": args.iters, "warmup": args.warmup,
@@ -82,6 +88,9 @@ def main():
         "rotate_ops_per_s": 1e3 / res["rotate_single_ms"],
         "rescale_ops_per_s": 1e3 / res["rescale_ms"],
         "ntt_glimbs_per_s_fwd_inv_avg": 2 * L * N / (res["ntt_fwd_plus_inv_ms"] / 1e3) / 1e9,
+        "csprng_randint_gsamples_per_s": len(engine.ckksCfg.q) * N / (res["csprng_randint_allP_ms"] / 1e3) / 1e9,
+        "encodecrypt_ops_per_s": 1e3 / res["encodecrypt_ms"],
+        "decryptcode_ops_per_s": 1e3 / res["decryptcode_ms"],
         **res,
         "note": "unmodified tiberate 0.9.11 engine + its CUDA extension (sm_100 build), one ciphertext per call, "
                 "CUDA events with synchronisation",

@@ -213,6 +213,16 @@ def run_ours(args):
     def hmult():
         ctx.cc_mult_relin(0, a0, a1, b0, b1, evk, out0, out1, True)
 
+    def timed_local(fn, k, w):  # this rank only (no barrier): host-inclusive wall time per call, ms
+        for _ in range(w):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / k
+
     sampler = ClockSampler(local)
     launches0 = lib.tb200_launch_count()
     if rank == 0:
@@ -239,6 +249,31 @@ def run_ours(args):
         ms_rs = timed(lambda: ctx.rescale(0, a0, a1, out0, out1), k2, 1)
         extra["rescale_ops_per_s"] = world * B * k2 / (ms_rs / 1e3)
         del r0, r1
+        # CSPRNG kernels (uniform residues for all P limbs = one `a` polynomial of a
+        # public key; algorithmic bytes per sample: 36 B of state traffic per 4 samples + 8 B out) and
+        # the self-contained engine path (keygen, encodecrypt) -- rank 0 only, small
+        if rank == 0:
+            from tiberate_fhe_b200 import CkksEngine
+
+            eng = CkksEngine(16, devices=[f"cuda:{local}"], chunk=args.chunk)
+            q_all = [list(eng.ctx.q)]
+            ms_r = timed_local(lambda: eng.rng.randint(q_all, repeats=eng.ctx.K), 20, 3)
+            samples = eng.ctx.P * N
+            extra["csprng_randint_gsamples_per_s"] = samples / (ms_r / 1e3) / 1e9
+            extra["csprng_randint_gbytes_per_s"] = samples * (144.0 / 4 + 8) / (ms_r / 1e3) / 1e9
+            ms_g = timed_local(lambda: eng.rng.discrete_gaussian(repeats=2), 20, 3)
+            extra["csprng_gaussian_gsamples_per_s"] = 2 * N / (ms_g / 1e3) / 1e9
+            t0 = time.perf_counter()
+            _ = eng.sk, eng.pk, eng.evk
+            torch.cuda.synchronize()
+            extra["keygen_sk_pk_evk_ms"] = (time.perf_counter() - t0) * 1e3
+            msg = torch.randn(eng.num_slots, dtype=torch.float64)
+            ms_e = timed_local(lambda: eng.encodecrypt(msg), 10, 2)
+            extra["encodecrypt_ops_per_s"] = 1e3 / ms_e
+            ct_e = eng.encodecrypt(msg)
+            ms_d = timed_local(lambda: eng.decryptcode(ct_e), 10, 2)
+            extra["decryptcode_ops_per_s"] = 1e3 / ms_d
+            del eng, ct_e
 
     # ---- per-kernel time inside the step (CUDA events around every launch, separate pass) ----------
     lib.tb200_prof_enable(1)
