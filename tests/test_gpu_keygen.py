@@ -138,6 +138,9 @@ def test_readme_scenario_matches_the_reference_engine(preset):
         trip = engine.cc_mult(ct6, ct6, post_relin=False)
         rec["triplet"] = trip
         rec["encode_plain"] = engine.encode(half, level=1)
+        rec["level_up"] = engine.level_up(ct, 3)
+        rec["rotate_offset_5"] = engine.rotate_offset(ct5, 5)  # makes rotk[4] on the way: same CSPRNG draws
+        rec["negate"] = engine.negate(ct5)
         dec = [engine.decryptcode(ct6, is_real=True), engine.decryptcode(trip), engine.decryptcode(ct)]
         torch.cuda.synchronize()
         return rec, [np.asarray(d) for d in dec]
@@ -151,6 +154,7 @@ def test_readme_scenario_matches_the_reference_engine(preset):
             assert x.shape == y.shape and torch.equal(x, y), f"{name}[{i}] differs from the reference engine"
     for i, (x, y) in enumerate(zip(wdec, gdec)):
         assert x.shape == y.shape and np.array_equal(x, y), f"decryptcode output {i} differs"
+    assert torch.equal(ref.rng.states[0], ours.rng.states[0]), "CSPRNG consumption differs"
     # and the numbers mean what they should: ((d*d + d)^2 * 2) rotated by one slot
     d = data.numpy()
     expect = np.roll(2 * (d * d + d) ** 2, -1)

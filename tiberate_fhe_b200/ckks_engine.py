@@ -23,7 +23,7 @@ import torch
 
 from . import wrapper
 from .context import KeySwitchKeyView, Tb200Context, galois_element
-from .keygen import CodecMixin, KeyGenMixin
+from .keygen import CodecMixin, KeyGenMixin, LevelMixin
 from .presets import PRESETS
 from .typing import FLAGS, Ciphertext, CiphertextTriplet, KeySwitchKey, Plaintext
 
@@ -45,7 +45,7 @@ class MontgomeryStateError(Exception):
         super().__init__(f"Montgomery state mismatch: expected MONTGOMERY_STATE={expected}")
 
 
-class CkksEngine(KeyGenMixin, CodecMixin):
+class CkksEngine(KeyGenMixin, CodecMixin, LevelMixin):
     def __init__(self, ckks_config=None, devices=None, *, chunk: int = 4, seed=None, nonce=None, bias_guard=True,
                  norm="forward"):
         """ckks_config: None (reference default: logN15 preset), an int logN naming a preset, or a dict

@@ -439,3 +439,80 @@ class CodecMixin:
             return ct
         return Ciphertext(data=[new_d0, [d.clone() for d in ct.data[1]]], flags=ct._flags, level=ct.level,
                           misc=dict(ct.misc))
+
+
+def decompose_with_power_of_2(a: int, n: int) -> list:
+    """Binary expansion of the offset a (mod n) (tiberate/utils/massive.py:83-98)."""
+    if n <= 0 or n & (n - 1):
+        raise AssertionError("n must be a power of 2")
+    a = a + n if a < 0 else a
+    return [1 << e for e in range(n.bit_length() - 1) if a & (1 << e)]
+
+
+def decompose_rot_offsets(offset: int, num_slots: int, rotks) -> list:
+    """Fewest-steps decomposition of `offset` over the rotation keys already made plus the powers of two
+    below num_slots / 2, never longer than the binary expansion (utils/massive.py:101-146): breadth-first
+    over partial sums in [-num_slots, num_slots], candidate steps in increasing order."""
+    from collections import deque
+
+    best = decompose_with_power_of_2(offset, num_slots)
+    steps = sorted(set(list(rotks.keys()) + [1 << i for i in range(int(math.log2(num_slots // 2)))]))
+    seen, queue = {0}, deque([(0, [])])
+    while queue:
+        total, path = queue.popleft()
+        if total == offset:
+            if len(path) <= len(best):
+                return path
+            break
+        for s in steps:
+            nxt = total + s
+            if -num_slots <= nxt <= num_slots and nxt not in seen:
+                seen.add(nxt)
+                queue.append((nxt, [*path, s]))
+    return best
+
+
+class LevelMixin:
+    """Level management and multi-step rotation: ckks_engine.py:1908-1926
+    (rotate_offset), :2086-2171 (level_up), :2473-2482 (negate)."""
+
+    def rotate_offset(self, ct: Ciphertext, offset: int, inplace: bool = True, return_decomposed_offsets=False):
+        if offset == 0:
+            return ct if inplace else ct.clone()
+        if offset in self.rotk:
+            return self.rotate_single(ct, self.rotk[offset])
+        offsets = decompose_rot_offsets(offset, self.num_slots, rotks=self.rotk)
+        for delta in offsets:
+            ct = self.rotate_single(ct, self.rotk[delta])
+        return (ct, offsets) if return_decomposed_offsets else ct
+
+    def level_up(self, ct: Ciphertext, dst_level: int, inplace=False) -> Ciphertext:
+        """Rescale once, drop to dst_level and multiply by round(scale * deviation ratio) so that the
+        message keeps the scale the destination level expects."""
+        import numpy as np
+
+        if ct.level == dst_level:
+            return ct if inplace else ct.clone()
+        new_ct = self.rescale(ct)
+        src_level = ct.level + 1
+        deviated_delta = round(self.scale * (self.deviations[dst_level] / np.sqrt(self.deviations[src_level])))
+        drop = dst_level - src_level
+        d0 = [new_ct.data[0][0][drop:]] if drop > 0 else new_ct.data[0]
+        d1 = [new_ct.data[1][0][drop:]] if drop > 0 else new_ct.data[1]
+        mult = [torch.tensor([(deviated_delta * (1 << 62)) % self.ctx.q[i] for i in self._primes(dst_level, -1)],
+                             dtype=torch.int64, device=self.device)]
+        K = self.ctx.K
+        mont_ops.mont_enter_scalar(d0, mult, K)
+        mont_ops.mont_enter_scalar(d1, mult, K)
+        mont_ops.reduce_2q(d0, K)
+        mont_ops.reduce_2q(d1, K)
+        return Ciphertext(data=[d0, d1], level=dst_level, logN=self.logN, misc=dict(new_ct.misc))
+
+    def negate(self, ct: Ciphertext, inplace: bool = False) -> Ciphertext:
+        if not inplace:
+            ct = ct.clone()
+        for part in ct.data:
+            for d in part:
+                d *= -1
+            mont_ops.make_signed(part, self.ctx.K)
+        return ct

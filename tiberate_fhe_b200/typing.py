@@ -61,6 +61,54 @@ class DataStruct:
                              misc=dict(self.misc))
         return new
 
+    # ---- on-disk format --------------------------------------------------------------
+    # The reference pickles the Python object (tiberate/typing.py:283-290), i.e. loading a file executes
+    # whatever the pickle says.  Here a file is a torch.save of plain containers -- class name, flags,
+    # level, metadata and the nested tensor lists -- readable with `weights_only=True`.
+    def _to_plain(self):
+        def pack(x):
+            if isinstance(x, DataStruct):
+                return {"__tb200__": x._to_plain()}
+            if isinstance(x, (list, tuple)):
+                return [pack(y) for y in x]
+            return x
+
+        misc = {k: v for k, v in self.misc.items() if isinstance(v, (int, float, str, bool, type(None)))}
+        return {"format": "tb200-datastruct-1", "cls": self.__class__.__name__, "flags": int(self._flags.value),
+                "level": int(self.level), "misc": misc, "data": pack(self.data)}
+
+    @classmethod
+    def _from_plain(cls, d):
+        def unpack(x):
+            if isinstance(x, dict) and "__tb200__" in x:
+                return DataStruct._from_plain(x["__tb200__"])
+            if isinstance(x, list):
+                return [unpack(y) for y in x]
+            return x
+
+        if d.get("format") != "tb200-datastruct-1":
+            raise ValueError("not a tb200 data-structure file")
+        klass = _CLASSES.get(d["cls"])
+        if klass is None:
+            raise ValueError(f"unknown data-structure class {d['cls']!r}")
+        obj = klass.__new__(klass)
+        DataStruct.__init__(obj, unpack(d["data"]), flags=FLAGS(d["flags"]), level=d["level"], misc=d["misc"])
+        return obj
+
+    def save(self, path: str):
+        import torch
+
+        torch.save(self._to_plain(), path)
+
+    @classmethod
+    def load(cls, path: str, map_location=None):
+        import torch
+
+        obj = DataStruct._from_plain(torch.load(path, map_location=map_location, weights_only=True))
+        if cls is not DataStruct and not isinstance(obj, cls):
+            raise TypeError(f"{path} holds a {type(obj).__name__}, not a {cls.__name__}")
+        return obj
+
     @classmethod
     def wrap(cls, another: "DataStruct", **kwargs):
         return cls(another.data, flags=another._flags, level=another.level, misc=dict(another.misc), **kwargs)
@@ -134,3 +182,7 @@ class RotationKey(KeySwitchKey):
 
 class ConjugationKey(DataStruct):
     pass
+
+
+_CLASSES = {c.__name__: c for c in (Ciphertext, CiphertextTriplet, SecretKey, EvaluationKey, PublicKey, KeySwitchKey,
+                                    RotationKey, ConjugationKey)}
