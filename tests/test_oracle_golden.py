@@ -8,7 +8,7 @@ import pytest
 
 import golden_check
 
-FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.json")))
+FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_logN*.json")))
 
 
 @pytest.mark.skipif(not FILES, reason="no reference-extension fixtures committed yet")
