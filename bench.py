@@ -136,7 +136,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 (exact; 40-bit-prime butterflies as error-free FP64 products)", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": "logN16 preset, level 0, cc_mult(pre_rescale)+relinearize, 1 ciphertext pair per step",
                    "note": "the reference has no CPU path (GPU-only); this arm times the CPU oracle port of its "
                            "algorithm on the host cores (NumPy + C/OpenMP)"},
