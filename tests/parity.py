@@ -226,6 +226,25 @@ def check_ntt(s: Setup, level=0, with_special=True, batch=2):
     u = h.dev(neg)
     ctx.ntt(u, pr[0], False)
     eq(h, u, eng.ntt(neg, pr), "ntt_radix2 on negative lazy input")
+    # sparse inputs: zero / tiny products put the Montgomery representative on the boundary that the
+    # FP64 forward butterflies resolve through their integer fallback (ExactF64Pol)
+    sp = np.zeros_like(a[0])
+    sp[:, 1] = 1
+    sp[:, 7] = o.qa[np.asarray(pr)] - 1
+    sp[:, N // 2] = 2
+    for enter in (True, False):
+        u = h.dev(sp)
+        ctx.ntt(u, pr[0], enter)
+        eq(h, u, eng.enter_ntt(sp, pr) if enter else eng.ntt(sp, pr), f"forward NTT of a sparse polynomial (enter={enter})")
+    u = h.dev(np.zeros_like(a[0]))
+    ctx.ntt(u, pr[0], True)
+    eq(h, u, eng.enter_ntt(np.zeros_like(a[0]), pr), "forward NTT of zero")
+    # beyond the FP64 domain (|x| >= 2^50): the tile falls back to the integer butterflies
+    big = a[0].copy()
+    big[:, 3] += np.int64(1) << 52
+    u = h.dev(big)
+    ctx.ntt(u, pr[0], False)
+    eq(h, u, eng.ntt(big, pr), "ntt_radix2 on an input beyond 2^50")
     # unreduced sums of lazy values on the 40-bit limbs (documented domain of the mod-q route: |x| < 2^51)
     wide = want[0].copy()
     for r, g in enumerate(pr):

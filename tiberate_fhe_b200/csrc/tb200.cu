@@ -289,6 +289,8 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.qd = (double)qi;
       f.qinv = 1.0 / (double)qi;
       f.exd = f.ex > qi / 2 ? -(double)(qi - f.ex) : (double)f.ex;
+      f.Rcd = Rm > qi / 2 ? -(double)(qi - Rm) : (double)Rm;
+      f.pad_ = 0.0;
       {
         const u64 ninv = h_invmod_prime((u64)N, qi);
         f.exNd = ninv > qi / 2 ? -(double)(qi - ninv) : (double)ninv;

@@ -117,6 +117,9 @@ struct tb200_ctx {
     d.LA = LA;
     d.LB = LB;
     d.P = P;
+    d.fp = d_fp;
+    d.twd = d_twd;
+    d.x64 = fast;
     return d;
   }
 };

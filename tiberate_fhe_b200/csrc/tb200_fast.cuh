@@ -32,6 +32,7 @@ struct __align__(16) TbFastPrime {
   int f64;           // small prime whose butterflies run on the FP64 pipe (see FastF64Pol)
   double qd, qinv;   // q and 1/q as doubles
   double exd, exNd;  // ex and N^-1 mod q centred into (-q/2, q/2]
+  double Rcd, pad_;  // R mod q centred
 };
 
 namespace tb {
@@ -69,7 +70,8 @@ struct FastSmallPol {
   u64 q, q2;
   int logN;
   typedef TbTw2 TW;
-  static __device__ __forceinline__ TW load(const TW* t) { return load_tw2(t); }
+  typedef TbTw2 TWS;
+  static __device__ __forceinline__ TW load(const TWS* t) { return load_tw2(t); }
   __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
     const u64 u = (u64)U, v = shoup_lazy((u64)O, S.w, S.ws, q);  // v < 4q
     U = (i64)(u + v);
@@ -101,7 +103,8 @@ struct FastSmallPol {
 struct FastF64Pol {
   double q, qinv;
   typedef double TW;
-  static __device__ __forceinline__ TW load(const TW* t) { return __ldg(t); }
+  typedef double TWS;
+  static __device__ __forceinline__ TW load(const TWS* t) { return __ldg(t); }
   static __device__ __forceinline__ double round_int(double x_plus_magic) { return __dadd_rn(x_plus_magic, -TB_F64_MAGIC); }
   // exact integer (|x| < 2^51) <-> double without the conversion unit
   // (the magic's low word is zero: one 32-bit add on the high word)
@@ -134,11 +137,62 @@ struct FastF64Pol {
   }
 };
 
+// The reference's lazy Montgomery butterfly (bfly_ct: V = MM(S, O); CS2(U + V), CS2(U + 2q - V)) with its
+// EXACT representatives, on the FP64 pipe, for q < 2^42 and |values| < 2^50.
+// MM(a, b) = floor(a b / 2^62) + floor(s q / 2^62) + [a b mod 2^62 != 0]  (tb200_mont.cuh) lies in
+// [xh, xh + q] with xh = floor(a b / 2^62) and is congruent to r = a b 2^-62 mod q, so it IS the canonical
+// residue r whenever xh < r < q + min(xh, 0): with |xh| <= |a| q 2^-62 + 1 (a few thousand for lazy inputs
+// against q ~ 2^40) that is all but ~2^-20 of the cases; r comes from one error-free FP64 product with the
+// plain twiddle w = S 2^-62 mod q.  The remaining cases take the integer Montgomery product (cold branch,
+// twiddle fetched from the integer table at the same index).  Bit-identical to ExactPol by construction.
+// out of line: 64 inlined copies of the integer product per tile would cost registers and I-cache for a
+// branch taken about once per million butterflies
+__device__ __noinline__ double exact_mm_cold(double O, const u64* s4, u64 q4, u64 k) {
+  return FastF64Pol::from_int(tb_mm_s4(FastF64Pol::to_int(O), __ldg(s4), q4, k));
+}
+
+struct ExactF64Pol {
+  FastF64Pol f;
+  PrimeRegs p;
+  double q2, xbs;       // 2q, q * 2^-62
+  const double* twd;    // this prime's rows of the double / integer twiddle tables (same layout)
+  const u64* psi4;
+  struct TW {
+    double w;
+    const u64* s4;
+  };
+  typedef double TWS;
+  __device__ __forceinline__ TW load(const TWS* t) const {
+    TW r;
+    r.w = __ldg(t);
+    r.s4 = psi4 + (t - twd);
+    return r;
+  }
+  // MM(O, S) as a double; w = centred S 2^-62 mod q
+  __device__ __forceinline__ double mm(double O, double w, const u64* s4) const {
+    double r = f.mulmod(O, w);
+    r = r < 0.0 ? __dadd_rn(r, f.q) : r;
+    r = r >= f.q ? __dadd_rn(r, -f.q) : r;
+    const double xb = __fma_rn(O < 0.0 ? -O : O, xbs, 2.0);
+    if (!(r > xb && r < __dadd_rn(f.q, -xb)))  // rare: the representative depends on floor(O S / 2^62)
+      r = exact_mm_cold(O, s4, p.q4, p.k);
+    return r;
+  }
+  __device__ __forceinline__ void ct(i64& Ub, i64& Ob, TW S, int) const {
+    const double U = __longlong_as_double(Ub);
+    const double V = mm(__longlong_as_double(Ob), S.w, S.s4);
+    const double a = __dadd_rn(U, V), b = __dadd_rn(__dadd_rn(U, q2), -V);
+    Ub = __double_as_longlong(a >= q2 ? __dadd_rn(a, -q2) : a);
+    Ob = __double_as_longlong(b >= q2 ? __dadd_rn(b, -q2) : b);
+  }
+};
+
 // any q < 2^60: Harvey lazy butterflies, forward values in [0, 4q), inverse values in [0, 2q).
 struct FastBigPol {
   u64 q, q2;
   typedef TbTw2 TW;
-  static __device__ __forceinline__ TW load(const TW* t) { return load_tw2(t); }
+  typedef TbTw2 TWS;
+  static __device__ __forceinline__ TW load(const TWS* t) { return load_tw2(t); }
   __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
     u64 u = (u64)U;
     u = (u >= q2) ? u - q2 : u;

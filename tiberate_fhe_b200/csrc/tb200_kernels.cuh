@@ -9,6 +9,7 @@
 //     128-byte lines), the pointwise kernels use 128-bit vector accesses, and the NTT kernels stage
 //     their tile in shared memory (tb200_ntt.cuh).
 #pragma once
+#include "tb200_fast.cuh"
 #include "tb200_ntt.cuh"
 #include "tb200_platform.h"
 
@@ -23,6 +24,11 @@ struct TbDev {
                        // stages of pass B stored transposed per tile, see tb::fwd_round<PERM>)
   const u64* ipsi4;    // [P][N] inverse twiddles
   int logN, LA, LB, P;
+  // forward transforms of the 40-bit limbs on the FP64 pipe with the reference's exact representatives
+  // (ExactF64Pol): enabled per context, per prime by TbFastPrime.f64
+  const TbFastPrime* fp;
+  const double* twd;
+  int x64;
 };
 
 // strided view of a batched polynomial
@@ -145,8 +151,36 @@ __global__ void __launch_bounds__(256) k_add_many(TbDev c, const i64* in, i64* o
 #define TB_EPI_EXIT_SIGNED 3   // ... ; make_signed    (intt_radix2_exit_reduce_signed)
 
 // forward pass A: stages 0..LA-1 on a tile of 2^LA rows x W columns (row = index >> LB).
+__device__ __noinline__ double exact_enter_cold(i64 x, i64 Rs, u64 q4, u64 k) {
+  return tb::FastF64Pol::from_int(tb_mm_ss(x, Rs, q4, k));
+}
+// CTA-uniform: may this tile take ExactF64Pol?  (prime on the FP64 pipe and every residue below 2^50 in magnitude)
+__device__ __forceinline__ bool tile_fits_f64(const TbDev& c, int g, const i64 (&x)[16]) {
+  if (!c.x64 || !c.fp[g].f64) return false;
+  TB_KERNEL_SHARED int wide;
+  if (threadIdx.x == 0) wide = 0;
+  __syncthreads();
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) bad |= (x[i] >= (1ll << 50)) | (x[i] <= -(1ll << 50));
+  if (bad) wide = 1;
+  __syncthreads();
+  return wide == 0;
+}
+__device__ __forceinline__ tb::ExactF64Pol exact_f64_policy(const TbDev& c, int g, const tb::PrimeRegs& p, const u64* psi4) {
+  const TbFastPrime& F = c.fp[g];
+  tb::ExactF64Pol pol;
+  pol.f = tb::FastF64Pol{F.qd, F.qinv};
+  pol.p = p;
+  pol.q2 = F.qd + F.qd;
+  pol.xbs = F.qd * 2.168404344971008868e-19;  // 2^-62
+  pol.twd = c.twd + ((long)g << c.logN);
+  pol.psi4 = psi4 + ((long)g << c.logN);
+  return pol;
+}
+
 template <int LA, int PRO>
-__global__ void __launch_bounds__(256) k_ntt_fwd_A(TbDev c, TbView src, TbView dst, int prime0, int LW) {
+__global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbView dst, int prime0, int LW) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
@@ -158,12 +192,34 @@ __global__ void __launch_bounds__(256) k_ntt_fwd_A(TbDev c, TbView src, TbView d
   i64 x[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = s[(long)tb::tile_x(tr, i, f0) << c.LB];
+  auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
+  if (tile_fits_f64(c, g, x)) {
+    const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
+    const i64 Rs = c.pr[g].Rs;
+    const double Rc = c.fp[g].Rcd;  // R mod q, centred
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double v = tb::FastF64Pol::from_int(x[i]);
+      if constexpr (PRO == TB_PRO_ENTER) {  // MM(x, R^2) with its exact representative (see ExactF64Pol)
+        double r = pol.f.mulmod(v, Rc);
+        r = r < 0.0 ? __dadd_rn(r, pol.f.q) : r;
+        r = r >= pol.f.q ? __dadd_rn(r, -pol.f.q) : r;
+        const double xb = __fma_rn(v < 0.0 ? -v : v, pol.xbs, 2.0);
+        if (!(r > xb && r < __dadd_rn(pol.f.q, -xb))) r = exact_enter_cold(x[i], Rs, p.q4, p.k);
+        v = r;
+      }
+      x[i] = __double_as_longlong(v);
+    }
+    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, pol.twd, pol, slot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = tb::FastF64Pol::to_int(__longlong_as_double(x[i]));
+    return;
+  }
   if constexpr (PRO == TB_PRO_ENTER) {
     const i64 Rs = c.pr[g].Rs;
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = tb_mm_ss(x[i], Rs, p.q4, p.k);
   }
-  auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
   tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = x[i];
@@ -171,7 +227,7 @@ __global__ void __launch_bounds__(256) k_ntt_fwd_A(TbDev c, TbView src, TbView d
 
 // forward pass B: stages LA..logN-1 on contiguous 2^LB blocks; a CTA owns TE = blockDim*16 residues.
 template <int LB>
-__global__ void __launch_bounds__(256) k_ntt_fwd_B(TbDev c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256, 3) k_ntt_fwd_B(TbDev c, TbView src, TbView dst, int prime0) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -189,7 +245,16 @@ __global__ void __launch_bounds__(256) k_ntt_fwd_B(TbDev c, TbView src, TbView d
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
-  tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
+  if (tile_fits_f64(c, g, x)) {
+    const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(tb::FastF64Pol::from_int(x[i]));
+    tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, pol.twd, pol, slot);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = tb::FastF64Pol::to_int(__longlong_as_double(x[i]));
+  } else {
+    tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
+  }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];

@@ -50,8 +50,9 @@ __device__ __forceinline__ void bfly_gs(i64& U, i64& V, u64 S4, const PrimeRegs&
 // Butterfly policy of the exposed, bit-exact transforms: the reference's lazy Montgomery butterflies.
 struct ExactPol {
   PrimeRegs p;
-  typedef u64 TW;
-  static __device__ __forceinline__ TW load(const TW* t) { return __ldg(t); }
+  typedef u64 TW;   // twiddle as the butterflies take it
+  typedef u64 TWS;  // table element
+  static __device__ __forceinline__ TW load(const TWS* t) { return __ldg(t); }
   __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int /*mlog*/) const { bfly_ct(U, O, S, p); }
   __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int /*mlog*/) const { bfly_gs(U, V, S, p); }
 };
@@ -74,7 +75,7 @@ __host__ __device__ constexpr int num_rounds() {
 // 16-byte records (4 L1 wavefronts per warp instruction instead of 32).
 template <int LT, int R, class POL, bool PERM = false>
 __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlog_of_d0,
-                                          const typename POL::TW* __restrict__ tw, const POL& p) {
+                                          const typename POL::TWS* __restrict__ tw, const POL& p) {
   constexpr int f = fwd_field<LT>(R);
   constexpr int top = LT - 1 - 4 * R;
   constexpr int ns = (LT - 4 * R) > 4 ? 4 : (LT - 4 * R);
@@ -89,7 +90,7 @@ __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlo
     const int gs = perm ? T : 1;
 #pragma unroll
     for (int g = 0; g < (8 >> b); ++g) {       // distinct twiddles: register bits above b
-      const typename POL::TW S4 = POL::load(tw + base + g * gs);
+      const typename POL::TW S4 = p.load(tw + base + g * gs);
 #pragma unroll
       for (int l = 0; l < (1 << b); ++l) {     // register bits below b
         const int i = (g << (b + 1)) | l;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void fwd_round(i64 (&x)[16], int t, int tile, int mlo
 // One inverse round: the same field as forward round R, stages ascending in distance.
 template <int LT, int R, class POL, bool PERM = false>
 __device__ __forceinline__ void inv_round(i64 (&x)[16], int t, int tile, int mlog_of_d0,
-                                          const typename POL::TW* __restrict__ tw, const POL& p) {
+                                          const typename POL::TWS* __restrict__ tw, const POL& p) {
   constexpr int f = fwd_field<LT>(R);
   constexpr int top = LT - 1 - 4 * R;
   constexpr int ns = (LT - 4 * R) > 4 ? 4 : (LT - 4 * R);
@@ -117,7 +118,7 @@ __device__ __forceinline__ void inv_round(i64 (&x)[16], int t, int tile, int mlo
     const int gs = perm ? T : 1;
 #pragma unroll
     for (int g = 0; g < (8 >> b); ++g) {
-      const typename POL::TW S4 = POL::load(tw + base + g * gs);
+      const typename POL::TW S4 = p.load(tw + base + g * gs);
 #pragma unroll
       for (int l = 0; l < (1 << b); ++l) {
         const int i = (g << (b + 1)) | l;
@@ -143,7 +144,7 @@ __device__ __forceinline__ void exchange(i64 (&x)[16], i64* sm, int t, int fw, i
 // on exit with field fwd_field<LT>(NR-1) (== 0 unless LT == 4k where it is also 0).
 template <int LT, bool PERM = false, class POL, class SlotFn>
 __device__ __forceinline__ void tile_fwd(i64 (&x)[16], i64* sm, int t, int tile, int mlog_of_d0,
-                                         const typename POL::TW* __restrict__ tw, const POL& p, SlotFn slot) {
+                                         const typename POL::TWS* __restrict__ tw, const POL& p, SlotFn slot) {
   fwd_round<LT, 0, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
   if constexpr (num_rounds<LT>() > 1) {
     exchange(x, sm, t, fwd_field<LT>(0), fwd_field<LT>(1), slot);
@@ -158,7 +159,7 @@ __device__ __forceinline__ void tile_fwd(i64 (&x)[16], i64* sm, int t, int tile,
 // Full inverse tile: rounds NR-1..0.  Entry layout: field fwd_field<LT>(NR-1); exit: fwd_field<LT>(0).
 template <int LT, bool PERM = false, class POL, class SlotFn>
 __device__ __forceinline__ void tile_inv(i64 (&x)[16], i64* sm, int t, int tile, int mlog_of_d0,
-                                         const typename POL::TW* __restrict__ tw, const POL& p, SlotFn slot) {
+                                         const typename POL::TWS* __restrict__ tw, const POL& p, SlotFn slot) {
   if constexpr (num_rounds<LT>() > 2) {
     inv_round<LT, 2, POL, PERM>(x, t, tile, mlog_of_d0, tw, p);
     exchange(x, sm, t, fwd_field<LT>(2), fwd_field<LT>(1), slot);

@@ -43,6 +43,7 @@ void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body);
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ inline __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define TB_KERNEL_SHARED static
