@@ -797,7 +797,8 @@ static TbView rows_from(TbView v, int r) {
   return v;
 }
 static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, TbView src, TbView dst, int rows,
-                              int batch, int prime0, tb200_stream st, bool wide_in = false) {
+                              int batch, int prime0, tb200_stream st, bool wide_in = false,
+                              const TbKsLevel* skip_lv = nullptr) {
   const int te = c->N < TB_TILE ? c->N : TB_TILE;
   // A CTA can walk over `bper` batch entries of one (limb, tile) to keep its twiddles in L1.  Measured
   // on B200 (logN16, chunk 16): bper = 8..16 is 12 % SLOWER than one entry per CTA at 2 or 3 CTAs/SM
@@ -816,7 +817,7 @@ static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, Tb
       LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
     } else {                                                                                     \
       auto kfn = k_fast_fwd_B<n, F>;                                                             \
-      LAUNCHN("k_fast_fwd_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
+      LAUNCHN("k_fast_fwd_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper, skip_lv); \
     }                                                                                            \
   } break;
     BCASE(4, false) BCASE(5, false) BCASE(6, false) BCASE(7, false) BCASE(8, false)
@@ -829,13 +830,13 @@ static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, Tb
 }
 // FP64 rows and integer rows go to separate launches: the FP64-only kernels need 64 registers (4 CTAs per SM)
 static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
-                         tb200_stream st, bool wide_in = false) {
+                         tb200_stream st, bool wide_in = false, const TbKsLevel* skip_lv = nullptr) {
   const int nf = f64_prefix(c, prime0, rows);
   int rc = 0;
-  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st, wide_in))) return rc;
+  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st, wide_in, skip_lv))) return rc;
   if (nf < rows)
     rc = launch_fast_B_rows(c, inverse, false, rows_from(src, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st,
-                            wide_in);
+                            wide_in, skip_lv);
   return rc;
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
@@ -1032,8 +1033,9 @@ static int ks_digits(tb200_ctx* c, int level, int nb, TbView a, TbView state, tb
 
 // key switch, part 2: from the complete digit state to the (local) output rows.
 // tail: 0 -> out0 = ks0 ; 1 -> out = CS1(add + ks) for both ; 2 -> out0 = CS1(CS2(add0 + ks0)), out1 = ks1
+// own_prefilled: the caller already wrote the (group, own limb) extensions in NTT form (k_fast_own_fill)
 static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskDev& key, TbView add0, TbView add1,
-                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st) {
+                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, bool own_prefilled = false) {
   const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
   const TbKsLevel& lv = c->ks[level];
   const int ng = lv.ngroups;
@@ -1053,8 +1055,11 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     fa.lenterd = c->d_lenterd;
     fa.prime0 = p0;
     fa.ngroups = ng;
+    fa.skip_own = own_prefilled ? 1 : 0;
     if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) return rc;
-    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, st))) return rc;
+    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, st, false,
+                            own_prefilled ? dlv : nullptr)))
+      return rc;
     // key inner product, 128-bit accumulation over the groups
     LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),
            dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb);
@@ -1084,12 +1089,12 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
 
 // key switch of `nb` polynomials (nb <= chunk) on an unsharded context. a: coefficient canonical [L][N].
 static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKskDev& key, TbView add0, TbView add1,
-                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st) {
+                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, bool own_prefilled = false) {
   const int S = c->ks[level].state_rows;
   TbView state = dense(ws, S, c->N);
   int rc = ks_digits(c, level, nb, a, state, st);
   if (rc) return rc;
-  return ks_finish(c, level, nb, state, key, add0, add1, out0, out1, tail, ws + (size_t)nb * S * c->N, st);
+  return ks_finish(c, level, nb, state, key, add0, add1, out0, out1, tail, ws + (size_t)nb * S * c->N, st, own_prefilled);
 }
 
 extern "C" int tb200_ks_state_info(const tb200_ctx* c, int level, int32_t* out) {
@@ -1297,11 +1302,18 @@ static int relin_chunk(tb200_ctx* c, int lvl, int nb, i64* d, const TbKskDev& ke
                        tb200_stream st) {
   const int N = c->N, L = c->num_ord - lvl;
   const size_t pe = (size_t)nb * L * N;
+  const bool reuse = c->fast && c->world == 1;
+  if (reuse) {  // NTT-domain d2 = forward transform of every group's extension at its own limbs (k_fast_own_fill)
+    i64* ext = ksws + (size_t)nb * c->ks[lvl].state_rows * N;  // where keyswitch_chunk / ks_finish put it
+    LAUNCH(k_fast_own_fill, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)L, (unsigned)nb),
+           dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), c->devf(), (const TbKsLevel*)(c->d_ks + lvl),
+           dense(d + 2 * pe, L, N), ext, lvl, N, L + c->K);
+  }
   int rc = c->fast ? fast_inverse_exit(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, st)
                    : ntt_inverse(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, 2, st);
   if (rc) return rc;
   return keyswitch_chunk(c, lvl, nb, dense(d + 2 * pe, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1, 1,
-                         ksws, st);
+                         ksws, st, reuse);
 }
 
 extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200_poly* d0, const tb200_poly* d1,

@@ -45,6 +45,7 @@ struct TbFwdAArgs {
   const u64* lenter2;     // EXTEND: (C, C') pairs, indexed (G.lenter_off + (k-1) P + prime)
   const double* lenterd;  // EXTEND, FP64 limbs: L_{k-1} mod q centred (no Montgomery factor), same indexing
   int prime0, LW, ngroups;
+  int skip_own;           // EXTEND: the (group, own limb) pairs were pre-filled by k_fast_own_fill
 };
 
 template <int PRO>
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   i64 x[16];
   if constexpr (PRO == TB_FPRO_EXTEND) {
     const TbKsGroup& G = a.lv->g[gi];
+    if (a.skip_own && g >= G.src_prime0 && g < G.src_prime0 + G.alpha) return;  // CTA-uniform
     if (P.f64) {
       extend_prologue_f64(x, a, P, G, bt, g, c.P, tr, f0, LB, c0);
     } else {
@@ -228,10 +230,15 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
 // the integer policies the kernel fits 64 registers and a fourth CTA per SM.
 template <int LB, bool F64ONLY>
 __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst,
-                                                                               int prime0, int batch, int bper) {
+                                                                               int prime0, int batch, int bper,
+                                                                               const TbKsLevel* skip_lv) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
+  if (skip_lv) {  // key-switch extension whose (group, own limb) pairs were pre-filled (k_fast_own_fill)
+    const TbKsGroup& G = skip_lv->g[blockIdx.z % skip_lv->ngroups];
+    if (g >= G.src_prime0 && g < G.src_prime0 + G.alpha) return;
+  }
   const TbFastPrime P = c.fp[g];
   const long e0 = (long)blockIdx.x * nt * 16;
   const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
@@ -374,6 +381,33 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
     const u64 y = tb::shoup((u64)x[i], P.ex, P.ex_s, P.q);
     d[(unsigned)tb::tile_x(tr, i, f0) << LB] = (i64)(y >= P.q ? y - P.q : y);
   }
+}
+
+// Relinearisation shortcut.  The mixed-radix digits of a digit group reconstruct the key-switch input modulo
+// each of the group's OWN primes, so the extension of group g at its own limb t is the input itself, and
+// its forward transform is the NTT-domain d2 limb the tensor product already produced: those L of the
+// beta (L+K) (group, limb) pairs skip ModUp and both forward passes.  d2 carries the Montgomery factor;
+// FP64 limbs keep their extensions without it and canonical (extend_prologue_f64), other limbs with it.
+__global__ void __launch_bounds__(256) k_fast_own_fill(TbDev c, TbDevFast f, const TbKsLevel* lv, TbView d2, i64* ext,
+                                                       int level, int N, int rowsE) {
+  const int r = blockIdx.y, bt = blockIdx.z, g = level + r;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (j >= N) return;
+  const int ng = lv->ngroups;
+  int gi = 0;
+  while (gi < ng && !(g >= lv->g[gi].src_prime0 && g < lv->g[gi].src_prime0 + lv->g[gi].alpha)) ++gi;
+  if (gi == ng) return;
+  longlong2 v = *reinterpret_cast<const longlong2*>(d2.row(bt, r) + j);
+  if (f.fp[g].f64) {
+    const TbPrime& P = c.pr[g];
+    v.x = tb_mr(v.x, P.q4, P.k);
+    v.y = tb_mr(v.y, P.q4, P.k);
+    v.x = v.x < 0 ? v.x + P.q : v.x;
+    v.y = v.y < 0 ? v.y + P.q : v.y;
+    v.x = v.x >= P.q ? v.x - P.q : v.x;
+    v.y = v.y >= P.q ? v.y - P.q : v.y;
+  }
+  *reinterpret_cast<longlong2*>(ext + (((long)bt * ng + gi) * rowsE + r) * N + j) = v;
 }
 
 // Montgomery reduction of a signed 128-bit T (|T| < 2^124): (T + ((T k) mod 2^62) q) / 2^62
