@@ -133,6 +133,7 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   cudaFree(c->d_resc3);
   cudaFree(c->d_lenter2);
   cudaFree(c->d_lenterd);
+  cudaFree(c->d_cP);
   cudaFree(c->d_bn);
   cudaFree(c->ws);
   delete c;
@@ -323,6 +324,14 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
     }
   for (int kk = 0; kk < K; ++kk)
     for (int row = 0; row < kk; ++row) pirsp[(size_t)kk * K + row] = pir[(size_t)kk * P + no + row];
+  std::vector<i64> cP((size_t)2 * P, 0);
+  for (int g = 0; g < P; ++g) {
+    const u64 qq = (u64)q[g];
+    u64 pp = 1 % qq;
+    for (int kk = 0; kk < K; ++kk) pp = h_mulmod(pp, (u64)q[no + kk] % qq, qq);
+    cP[g] = (i64)pp;
+    cP[(size_t)P + g] = (i64)h_mulmod(pp, (u64)(Rbig % qq), qq);
+  }
   // ModDown in product form: B_k = prod_{j<=k} P_j^-1 mod q_g
   std::vector<u64> bn((size_t)(K + 1) * P * 2, 0);
   for (int g = 0; g < no; ++g) {
@@ -435,7 +444,7 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
             ((c->fps = fps), upload(&c->d_fp, fps)) == cudaSuccess && upload(&c->d_tw, tw2) == cudaSuccess &&
             upload(&c->d_itw, itw2) == cudaSuccess && upload(&c->d_twd, twd) == cudaSuccess &&
             upload(&c->d_itwd, itwd) == cudaSuccess && upload(&c->d_resc3, resc3) == cudaSuccess &&
-            upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_lenterd, lenterd) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
+            upload(&c->d_lenter2, lenter2) == cudaSuccess && upload(&c->d_lenterd, lenterd) == cudaSuccess && upload(&c->d_cP, cP) == cudaSuccess && upload(&c->d_bn, bn) == cudaSuccess;
   if (!ok) {
     fail(TB200_ENOMEM, "ctx_create: device allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     tb200_ctx_destroy(c);
@@ -1033,9 +1042,16 @@ static int ks_digits(tb200_ctx* c, int level, int nb, TbView a, TbView state, tb
 
 // key switch, part 2: from the complete digit state to the (local) output rows.
 // tail: 0 -> out0 = ks0 ; 1 -> out = CS1(add + ks) for both ; 2 -> out0 = CS1(CS2(add0 + ks0)), out1 = ks1
-// own_prefilled: the caller already wrote the (group, own limb) extensions in NTT form (k_fast_own_fill)
+// Relinearisation extras of the mod-q path: own_prefilled = the caller already wrote the (group, own limb)
+// extensions in NTT form (k_fast_own_fill); nadd0/nadd1 = NTT-domain d0/d1 (dense [nb][L][N]) folded into
+// the key inner product instead of being added after ModDown (k_fast_mac).
+struct TbRelinExtra {
+  bool own_prefilled;
+  const i64 *nadd0, *nadd1;
+};
 static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskDev& key, TbView add0, TbView add1,
-                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, bool own_prefilled = false) {
+                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, const TbRelinExtra* ex = nullptr) {
+  const bool own_prefilled = ex && ex->own_prefilled;
   const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
   const TbKsLevel& lv = c->ks[level];
   const int ng = lv.ngroups;
@@ -1062,7 +1078,9 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
       return rc;
     // key inner product, 128-bit accumulation over the groups
     LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),
-           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb);
+           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb,
+           ex ? ex->nadd0 : (const i64*)nullptr, ex ? ex->nadd1 : (const i64*)nullptr, (const i64*)c->d_cP);
+    if (ex && ex->nadd0) tail = 0;  // already inside the sums
     // back to coefficients, canonical
     if ((rc = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, st, 1))) return rc;
   } else {
@@ -1089,12 +1107,13 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
 
 // key switch of `nb` polynomials (nb <= chunk) on an unsharded context. a: coefficient canonical [L][N].
 static int keyswitch_chunk(tb200_ctx* c, int level, int nb, TbView a, const TbKskDev& key, TbView add0, TbView add1,
-                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, bool own_prefilled = false) {
+                           TbView out0, TbView out1, int tail, i64* ws, tb200_stream st,
+                           const TbRelinExtra* ex = nullptr) {
   const int S = c->ks[level].state_rows;
   TbView state = dense(ws, S, c->N);
   int rc = ks_digits(c, level, nb, a, state, st);
   if (rc) return rc;
-  return ks_finish(c, level, nb, state, key, add0, add1, out0, out1, tail, ws + (size_t)nb * S * c->N, st, own_prefilled);
+  return ks_finish(c, level, nb, state, key, add0, add1, out0, out1, tail, ws + (size_t)nb * S * c->N, st, ex);
 }
 
 extern "C" int tb200_ks_state_info(const tb200_ctx* c, int level, int32_t* out) {
@@ -1309,11 +1328,18 @@ static int relin_chunk(tb200_ctx* c, int lvl, int nb, i64* d, const TbKskDev& ke
            dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), c->devf(), (const TbKsLevel*)(c->d_ks + lvl),
            dense(d + 2 * pe, L, N), ext, lvl, N, L + c->K);
   }
+  if (reuse) {  // d0 / d1 stay in the NTT domain and enter the key inner product (k_fast_mac)
+    int rc = fast_inverse_exit(c, dense(d + 2 * pe, L, N), dense(d + 2 * pe, L, N), L, nb, lvl, st);
+    if (rc) return rc;
+    const TbRelinExtra ex = {true, d, d + pe};
+    return keyswitch_chunk(c, lvl, nb, dense(d + 2 * pe, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1,
+                           1, ksws, st, &ex);
+  }
   int rc = c->fast ? fast_inverse_exit(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, st)
                    : ntt_inverse(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, 2, st);
   if (rc) return rc;
   return keyswitch_chunk(c, lvl, nb, dense(d + 2 * pe, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1, 1,
-                         ksws, st, reuse);
+                         ksws, st);
 }
 
 extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200_poly* d0, const tb200_poly* d1,

@@ -90,6 +90,7 @@ struct tb200_ctx {
   TbTw2 *d_tw = nullptr, *d_itw = nullptr;
   double *d_twd = nullptr, *d_itwd = nullptr;  // centred double twiddles, same layout
   u64* d_resc3 = nullptr;    // [num_ord][P][3]: (q_l^-1 R mod q_g, Shoup companion, offset) per (level l, prime g)
+  i64* d_cP = nullptr;       // [2][P]: P mod q, P R mod q (P = product of the special primes): relinearisation tail in the MAC
   u64* d_bn = nullptr;       // ModDown: [(K+1)][P][2] (-B_k mod q, Shoup) k < K, then (B_{K-1}, Shoup)
   double* d_lenterd = nullptr; // L_{k-1} mod q_g centred doubles, same indexing as d_lenter
   u64* d_lenter2 = nullptr;  // (L_{k-1} R mod q_g, Shoup companion) pairs, same indexing as d_lenter

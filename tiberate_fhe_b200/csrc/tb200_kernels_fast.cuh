@@ -427,8 +427,13 @@ __device__ __forceinline__ i64 tb_norm2q(i64 x, i64 q2) {
 
 // key inner product, mod q: small primes accumulate the 128-bit products over the digit groups and
 // reduce once; other primes reduce per term.  Output lazy residues in [0, 2q + small).
+// Relinearisation tail fused in (nadd0 != nullptr): the NTT-domain d0 / d1 limbs, times P = prod of the
+// special primes, are added to the ordinary limbs of the two sums -- ModDown then returns ks + d exactly
+// ((x + P d - [x]_P) / P = (x - [x]_P) / P + d), so d0 and d1 need no inverse transform of their own.
+// cP: [2][nP] = P mod q (limbs whose sums carry no Montgomery factor: FP64 limbs) and P R mod q (others).
 __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
-                                                  const i64* ext, i64* acc, int level, int N, int rowsE, int nb) {
+                                                  const i64* ext, i64* acc, int level, int N, int rowsE, int nb,
+                                                  const i64* nadd0, const i64* nadd1, const i64* cP) {
   // grid.x = nb * tiles with the batch index fastest: the nb ciphertexts of a chunk read the same key
   // tile back to back, so the key is fetched from HBM once per chunk (L2 serves the rest)
   const int t = blockIdx.y, bt = blockIdx.x % nb;
@@ -438,6 +443,19 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
   if (j >= N) return;
   const int ng = lv->ngroups;
   longlong2 o0, o1;
+  // relinearisation tail: issued first so that these loads overlap the group loop
+  const bool has_add = nadd0 != nullptr && t < lv->L;
+  i64 add0x = 0, add0y = 0, add1x = 0, add1y = 0;
+  if (has_add) {
+    const i64 cp = cP[(f.fp[level + t].f64 ? 0 : f.P) + level + t];
+    const long at = ((long)bt * lv->L + t) * N + j;
+    const longlong2 u0 = *reinterpret_cast<const longlong2*>(nadd0 + at);
+    const longlong2 u1 = *reinterpret_cast<const longlong2*>(nadd1 + at);
+    add0x = tb_mm_ss(u0.x, cp, P.q4, P.k);
+    add0y = tb_mm_ss(u0.y, cp, P.q4, P.k);
+    add1x = tb_mm_ss(u1.x, cp, P.q4, P.k);
+    add1y = tb_mm_ss(u1.y, cp, P.q4, P.k);
+  }
   if (small) {
     // lazy residue (< 2^49) times key residue (|k| < 2^42): |term| < 2^91, the sum over <= 32 groups fits 128 bits.
     // Two digit groups per iteration so that six 16-byte loads are in flight per thread (the kernel
@@ -490,6 +508,18 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
     o0.y = a0y;
     o1.x = a1x;
     o1.y = a1y;
+  }
+  if (has_add) {
+    o0.x += add0x;
+    o0.y += add0y;
+    o1.x += add1x;
+    o1.y += add1y;
+    if (!small) {  // the 60-bit inverse butterflies expect [0, 2q)
+      o0.x = tb_norm2q(o0.x, P.q2);
+      o0.y = tb_norm2q(o0.y, P.q2);
+      o1.x = tb_norm2q(o1.x, P.q2);
+      o1.y = tb_norm2q(o1.y, P.q2);
+    }
   }
   *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 0) * rowsE + t) * N + j) = o0;
   *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 1) * rowsE + t) * N + j) = o1;
