@@ -291,11 +291,12 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.qinv = 1.0 / (double)qi;
       f.exd = f.ex > qi / 2 ? -(double)(qi - f.ex) : (double)f.ex;
       f.Rcd = Rm > qi / 2 ? -(double)(qi - Rm) : (double)Rm;
-      f.pad_ = 0.0;
       {
-        const u64 ninv = h_invmod_prime((u64)N, qi);
-        f.exNd = ninv > qi / 2 ? -(double)(qi - ninv) : (double)ninv;
+        u64 pp = 1 % qi;
+        for (int kk = 0; kk < K; ++kk) pp = h_mulmod(pp, (u64)q[no + kk] % qi, qi);
+        f.cPd = pp > qi / 2 ? -(double)(qi - pp) : (double)pp;
       }
+      f.pad0_ = 0.0;
     }
   }
   // rescale scales and P_k^-1 tables
@@ -734,6 +735,9 @@ extern "C" int tb200_ntt(tb200_ctx* c, int rows, int batch, int prime0, const tb
 }
 static int fast_inverse_exit(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
                              tb200_stream st, int mac_chain = 0, bool wide_in = false);
+// inverse pass B' input modes: lazy integers in (-2q, 2q); any |x| < 2^51 on the FP64 limbs (exposed intt);
+// doubles on the FP64 limbs (output of the FP64 key inner product)
+enum { TB_INV_IN_LAZY = 0, TB_INV_IN_WIDE = 1, TB_INV_IN_DOUBLE = 2 };
 extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const tb200_poly* a, int mode,
                           tb200_stream st) {
   if (!c) return fail(TB200_EINVAL, "null context");
@@ -806,8 +810,8 @@ static TbView rows_from(TbView v, int r) {
   return v;
 }
 static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, TbView src, TbView dst, int rows,
-                              int batch, int prime0, tb200_stream st, bool wide_in = false,
-                              const TbKsLevel* skip_lv = nullptr) {
+                              int batch, int prime0, tb200_stream st, int in_mode = 0,
+                              const TbKsLevel* skip_lv = nullptr, int dbl_out = 0) {
   const int te = c->N < TB_TILE ? c->N : TB_TILE;
   // A CTA can walk over `bper` batch entries of one (limb, tile) to keep its twiddles in L1.  Measured
   // on B200 (logN16, chunk 16): bper = 8..16 is 12 % SLOWER than one entry per CTA at 2 or 3 CTAs/SM
@@ -818,15 +822,18 @@ static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, Tb
   switch (c->LB * 2 + (f64only ? 1 : 0)) {
 #define BCASE(n, F)                                                                              \
   case n * 2 + (F ? 1 : 0): {                                                                    \
-    if (inverse && wide_in) {                                                                    \
-      auto kfn = k_fast_inv_B<n, F, true>;                                                       \
+    if (inverse && in_mode == TB_INV_IN_WIDE) {                                                  \
+      auto kfn = k_fast_inv_B<n, F, TB_INV_IN_WIDE>;                                             \
+      LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
+    } else if (inverse && in_mode == TB_INV_IN_DOUBLE) {                                         \
+      auto kfn = k_fast_inv_B<n, F, TB_INV_IN_DOUBLE>;                                           \
       LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
     } else if (inverse) {                                                                        \
-      auto kfn = k_fast_inv_B<n, F, false>;                                                      \
+      auto kfn = k_fast_inv_B<n, F, TB_INV_IN_LAZY>;                                             \
       LAUNCHN("k_fast_inv_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper);   \
     } else {                                                                                     \
       auto kfn = k_fast_fwd_B<n, F>;                                                             \
-      LAUNCHN("k_fast_fwd_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper, skip_lv); \
+      LAUNCHN("k_fast_fwd_B", kfn, grid, block, st, c->devf(), src, dst, prime0, batch, bper, skip_lv, dbl_out); \
     }                                                                                            \
   } break;
     BCASE(4, false) BCASE(5, false) BCASE(6, false) BCASE(7, false) BCASE(8, false)
@@ -839,13 +846,14 @@ static int launch_fast_B_rows(const tb200_ctx* c, bool inverse, bool f64only, Tb
 }
 // FP64 rows and integer rows go to separate launches: the FP64-only kernels need 64 registers (4 CTAs per SM)
 static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
-                         tb200_stream st, bool wide_in = false, const TbKsLevel* skip_lv = nullptr) {
+                         tb200_stream st, int in_mode = 0, const TbKsLevel* skip_lv = nullptr, int dbl_out = 0) {
   const int nf = f64_prefix(c, prime0, rows);
   int rc = 0;
-  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st, wide_in, skip_lv))) return rc;
+  if (nf > 0 && (rc = launch_fast_B_rows(c, inverse, true, src, dst, nf, batch, prime0, st, in_mode, skip_lv, dbl_out)))
+    return rc;
   if (nf < rows)
     rc = launch_fast_B_rows(c, inverse, false, rows_from(src, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st,
-                            wide_in, skip_lv);
+                            in_mode, skip_lv, dbl_out);
   return rc;
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
@@ -868,11 +876,11 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
   if (rc) return rc;
   return launch_fast_B(c, false, dst, dst, rows, batch, prime0, st);
 }
-// mac_chain: the input is the key inner product of an FP64-extended digit expansion, whose FP64 limbs
-// carry no Montgomery factor (extend_prologue_f64): their exit multiplies by N^-1 instead of N^-1 R^-1
+// mac_chain: the input is the output of k_fast_mac, whose FP64 limbs are doubles
 static int fast_inverse_exit(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
                              tb200_stream st, int mac_chain, bool wide_in) {
-  int rc = launch_fast_B(c, true, src, dst, rows, batch, prime0, st, wide_in);
+  int rc = launch_fast_B(c, true, src, dst, rows, batch, prime0, st,
+                         mac_chain ? TB_INV_IN_DOUBLE : (wide_in ? TB_INV_IN_WIDE : TB_INV_IN_LAZY));
   if (rc) return rc;
   return launch_fast_inv_A(c, dst, dst, rows, batch, prime0, mac_chain, st);
 }
@@ -1073,8 +1081,8 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     fa.ngroups = ng;
     fa.skip_own = own_prefilled ? 1 : 0;
     if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) return rc;
-    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, st, false,
-                            own_prefilled ? dlv : nullptr)))
+    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, st, 0,
+                            own_prefilled ? dlv : nullptr, 1)))
       return rc;
     // key inner product, 128-bit accumulation over the groups
     LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),

@@ -31,8 +31,8 @@ struct __align__(16) TbFastPrime {
   int small;         // q < 2^42
   int f64;           // small prime whose butterflies run on the FP64 pipe (see FastF64Pol)
   double qd, qinv;   // q and 1/q as doubles
-  double exd, exNd;  // ex and N^-1 mod q centred into (-q/2, q/2]
-  double Rcd, pad_;  // R mod q centred
+  double exd, pad0_;  // ex centred into (-q/2, q/2]
+  double Rcd, cPd;   // R mod q and P mod q (P = product of the special primes) centred
 };
 
 namespace tb {

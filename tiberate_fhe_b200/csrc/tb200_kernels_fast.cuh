@@ -114,8 +114,8 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
 
 // The same sums on the FP64 pipe, for a target limb that takes the FP64 butterflies -- WITHOUT the
 // Montgomery factor: x = d_0 + sum_{k>=1} d_k L_{k-1} mod q, so the first digit costs no product.
-// (The key inner product then yields x key instead of x key R, and k_fast_inv_A's exit multiplies
-// these limbs by N^-1 instead of N^-1 R^-1: `mac_chain`.)  A digit of a 40-bit source prime is a
+// (The key residues are in Montgomery form, so the FP64 key inner product x (key R) carries the factor
+// again and the usual exit N^-1 R^-1 applies.)  A digit of a 40-bit source prime is a
 // signed integer below 2^42 (a Montgomery product of k_digits) and enters FastF64Pol::mulmod directly;
 // a digit of a 60-bit source prime is split as hi * 2^30 + lo.  Every term is below max(2^42, 1.1 q)
 // in magnitude, so |x| < 2^47; x stays a double for the stages.
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
 template <int LB, bool F64ONLY>
 __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(TbDevFast c, TbView src, TbView dst,
                                                                                int prime0, int batch, int bper,
-                                                                               const TbKsLevel* skip_lv) {
+                                                                               const TbKsLevel* skip_lv, int dbl_out) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -257,7 +257,11 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(T
     if (F64ONLY || P.f64) {
       const tb::FastF64Pol pol{P.qd, P.qinv};
       tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.twd + ((long)g << c.logN), pol, slot);  // doubles from pass A
-      tile_f64_reduce<true>(x, pol);  // [0, q)
+      // [0, q) integers, or -- feeding the FP64 key inner product -- doubles in [-q/2 - 1, q/2 + 1]
+      if (dbl_out)
+        tile_f64_reduce<false>(x, pol);
+      else
+        tile_f64_reduce<true>(x, pol);
     } else if constexpr (!F64ONLY) {
       if (P.small) {
         tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
@@ -287,8 +291,9 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(T
 }
 
 // inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
-// WIDE_IN (the exposed tb200_intt): FP64 limbs accept any |x| < 2^51 and are reduced first.
-template <int LB, bool F64ONLY, bool WIDE_IN>
+// IN_MODE 1 (the exposed tb200_intt): FP64 limbs accept any |x| < 2^51 and are reduced first;
+// IN_MODE 2 (after k_fast_mac): FP64 limbs arrive as doubles (|x| < 16 q), reduced first.
+template <int LB, bool F64ONLY, int IN_MODE>
 __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(TbDevFast c, TbView src, TbView dst,
                                                                                int prime0, int batch, int bper) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(T
     for (int i = 0; i < 8; ++i) {
       const longlong2 v = sv[i * nt + tid];
       const int e = 2 * (i * nt + tid);
-      if (WIDE_IN && (F64ONLY || P.f64)) {
+      if (IN_MODE != 0 && (F64ONLY || P.f64)) {
         sm[tb::pad16(e)] = v.x;
         sm[tb::pad16(e + 1)] = v.y;
       } else {
@@ -326,8 +331,8 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(T
     for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, 0))];
     if (F64ONLY || P.f64) {  // inputs in [0, 4q): after the LB stages < 2^(LB+2) q < 2^52; renormalised before the store
       const tb::FastF64Pol pol{P.qd, P.qinv};
-      tile_to_f64(x);
-      if constexpr (WIDE_IN) tile_f64_reduce<false>(x, pol);
+      if constexpr (IN_MODE != 2) tile_to_f64(x);
+      if constexpr (IN_MODE != 0) tile_f64_reduce<false>(x, pol);
       tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, c.itwd + ((long)g << c.logN), pol, slot);
       tile_f64_reduce<false>(x, pol);  // stays double for pass A'
     } else if constexpr (!F64ONLY) {
@@ -362,7 +367,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
   if (P.f64) {  // inputs |x| <= q/2 + 1 (renormalised by inverse pass B'): < 2^(LA-1) q after the LA stages
     const tb::FastF64Pol pol{P.qd, P.qinv};
     tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, c.itwd + ((long)g << c.logN), pol, slot);
-    const double exd = mac_chain ? P.exNd : P.exd;
+    const double exd = P.exd;
+    (void)mac_chain;  // (kept in the signature: the input of this pass is the same either way)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       double r = pol.mulmod(__longlong_as_double(x[i]), exd);  // x N^-1 R^-1, |r| < 1.1 q
@@ -406,6 +412,8 @@ __global__ void __launch_bounds__(256) k_fast_own_fill(TbDev c, TbDevFast f, con
     v.y = v.y < 0 ? v.y + P.q : v.y;
     v.x = v.x >= P.q ? v.x - P.q : v.x;
     v.y = v.y >= P.q ? v.y - P.q : v.y;
+    v.x = __double_as_longlong(tb::FastF64Pol::from_int(v.x));  // FP64 limbs: the extensions are doubles
+    v.y = __double_as_longlong(tb::FastF64Pol::from_int(v.y));
   }
   *reinterpret_cast<longlong2*>(ext + (((long)bt * ng + gi) * rowsE + r) * N + j) = v;
 }
@@ -443,6 +451,45 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
   if (j >= N) return;
   const int ng = lv->ngroups;
   longlong2 o0, o1;
+  if (f.fp[level + t].f64) {
+    // FP64 limbs: extensions are doubles (k_fast_fwd_B dbl_out / k_fast_own_fill), the key residues
+    // (|k| < 2^51, Montgomery form) are converted on the fly; every term is an error-free modular product,
+    // |sum| < 12 q.  16 instructions per (residue, group) for both key halves against ~45 integer ones.
+    const TbFastPrime F = f.fp[level + t];
+    const tb::FastF64Pol pol{F.qd, F.qinv};
+    double s0x = 0.0, s0y = 0.0, s1x = 0.0, s1y = 0.0;
+    if (nadd0 != nullptr && t < lv->L) {  // + P d0, P d1 (NTT domain, Montgomery form like the key products)
+      const long at = ((long)bt * lv->L + t) * N + j;
+      const longlong2 u0 = *reinterpret_cast<const longlong2*>(nadd0 + at);
+      const longlong2 u1 = *reinterpret_cast<const longlong2*>(nadd1 + at);
+      s0x = pol.mulmod(tb::FastF64Pol::from_int(u0.x), F.cPd);
+      s0y = pol.mulmod(tb::FastF64Pol::from_int(u0.y), F.cPd);
+      s1x = pol.mulmod(tb::FastF64Pol::from_int(u1.x), F.cPd);
+      s1y = pol.mulmod(tb::FastF64Pol::from_int(u1.y), F.cPd);
+    }
+    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + j;
+    const long estride = (long)rowsE * N, koff = (long)(level + t) * key.rs + j;
+#pragma unroll 2
+    for (int gi = 0; gi < ng; ++gi) {
+      const int gid = lv->g[gi].gid;
+      const longlong2 e = *reinterpret_cast<const longlong2*>(ep);
+      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + koff);
+      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + koff);
+      ep += estride;
+      const double ex = __longlong_as_double(e.x), ey = __longlong_as_double(e.y);
+      s0x = __dadd_rn(s0x, pol.mulmod(ex, tb::FastF64Pol::from_int(kb.x)));
+      s0y = __dadd_rn(s0y, pol.mulmod(ey, tb::FastF64Pol::from_int(kb.y)));
+      s1x = __dadd_rn(s1x, pol.mulmod(ex, tb::FastF64Pol::from_int(ka.x)));
+      s1y = __dadd_rn(s1y, pol.mulmod(ey, tb::FastF64Pol::from_int(ka.y)));
+    }
+    o0.x = __double_as_longlong(s0x);
+    o0.y = __double_as_longlong(s0y);
+    o1.x = __double_as_longlong(s1x);
+    o1.y = __double_as_longlong(s1y);
+    *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 0) * rowsE + t) * N + j) = o0;
+    *reinterpret_cast<longlong2*>(acc + (((long)bt * 2 + 1) * rowsE + t) * N + j) = o1;
+    return;
+  }
   // relinearisation tail: issued first so that these loads overlap the group loop
   const bool has_add = nadd0 != nullptr && t < lv->L;
   i64 add0x = 0, add0y = 0, add1x = 0, add1y = 0;
