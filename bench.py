@@ -296,12 +296,13 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     # algorithmic limb passes (LP = N * 8 bytes) moved per HMult by each transform kernel:
     #   forward pass A: the 4 input polys (read L+1 limbs incl. the dropped one, write L) + ModUp (read the
-    #   L digit rows once, write ngroups * (L+K) extended limbs); forward pass B: read + write of the
-    #   4 L + ngroups (L+K) limbs; inverse passes: read + write of the 3 L + 2 (L+K) limbs.
+    #   L digit rows once, write the ngroups * (L+K) - L extended limbs that are not a group's own);
+    #   forward pass B: read + write of the 4 L + ngroups (L+K) - L limbs; inverse passes: read + write of
+    #   d2 (L limbs) and the two key sums (2 (L+K)) -- d0 / d1 stay in the NTT domain.
     E = L + K
-    fwd_limbs, inv_limbs = 4 * L + ng * E, 3 * L + 2 * E
+    fwd_limbs, inv_limbs = 4 * L + ng * E - L, L + 2 * E
     limbs = {"k_ntt_fwd_A": 2 * fwd_limbs, "k_ntt_fwd_B": 2 * fwd_limbs, "k_ntt_inv_A": 2 * inv_limbs,
-             "k_ntt_inv_B": 2 * inv_limbs, "k_fast_fwd_A": 4 * (2 * L + 1) + L + ng * E,
+             "k_ntt_inv_B": 2 * inv_limbs, "k_fast_fwd_A": 4 * (2 * L + 1) + L + ng * E - L,
              "k_fast_fwd_B": 2 * fwd_limbs, "k_fast_inv_A": 2 * inv_limbs, "k_fast_inv_B": 2 * inv_limbs}
     roof = None
     if top in limbs:
@@ -320,7 +321,11 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if roof and os.path.exists(tpath):
         with open(tpath) as f:
-            roof["traffic"] = json.load(f).get(roof["kernel"])
+            tj = json.load(f)
+        # ncu: (dram__bytes_read.sum + dram__bytes_write.sum) per launch / ciphertext pairs of the launch
+        per_ct = tj.get(roof["kernel"] + "_per_ciphertext_pair")
+        if per_ct is not None:
+            roof["traffic"] = per_ct * min(B, args.chunk)
 
     # ---- end to end: host (pinned) buffers -> C ABI -> host result, copies inside the timed region --
     # The batch is cut in sub-batches that flow through three streams (H2D, compute, D2H) with two
