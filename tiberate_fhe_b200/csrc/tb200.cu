@@ -756,12 +756,26 @@ extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const t
 }
 
 // ---- fast (mod-q) transforms ------------------------------------------------------------------------
-template <int PRO>
-static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gridz, tb200_stream st) {
+template <int PRO, bool F64ONLY>
+static int launch_fast_fwd_A_rows(const tb200_ctx* c, TbFwdAArgs a, int rows, int gridz, tb200_stream st) {
   const int lw = ntt_lw(c);
   a.LW = lw;
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)gridz), block(1u << (c->LA - 4 + lw));
   const bool big = c->LB == 8 && lw == 12 - c->LA;  // logN >= 12: compile-time strides
+  if constexpr (F64ONLY) {
+    switch (c->LA) {
+#define FCASE(n)                                                 \
+  case n: {                                                      \
+    auto kfn = k_fast_fwd_A<n, PRO, true, true>;                 \
+    LAUNCHN("k_fast_fwd_A", kfn, grid, block, st, c->devf(), a); \
+  } break;
+      FCASE(4) FCASE(5) FCASE(6) FCASE(7) FCASE(8) FCASE(9)
+#undef FCASE
+      default:
+        return fail(TB200_EINVAL, "unsupported LA %d (LB %d)", c->LA, c->LB);
+    }
+    return 0;
+  }
   switch (c->LA + (big ? 100 : 0)) {
 #define ACASE(n, B)                                                     \
   case n + (B ? 100 : 0): {                                             \
@@ -775,6 +789,25 @@ static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gri
       return fail(TB200_EINVAL, "unsupported LA %d (LB %d)", c->LA, c->LB);
   }
   return 0;
+}
+static int f64_prefix(const tb200_ctx* c, int prime0, int rows);
+static TbView rows_from(TbView v, int r);
+// The ModUp extend launch is split like pass B: the FP64 rows run an instantiation without the integer
+// prologue and butterflies (64 registers, 4 CTAs/SM), the remaining rows the generic kernel.
+template <int PRO>
+static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gridz, tb200_stream st) {
+  if constexpr (PRO == TB_FPRO_EXTEND) {
+    const int lw = ntt_lw(c);
+    const int nf = (c->LB == 8 && lw == 12 - c->LA) ? f64_prefix(c, a.prime0, rows) : 0;
+    if (nf > 0) {
+      int rc = launch_fast_fwd_A_rows<PRO, true>(c, a, nf, gridz, st);
+      if (rc || nf == rows) return rc;
+      a.prime0 += nf;
+      a.dst = rows_from(a.dst, nf);
+      return launch_fast_fwd_A_rows<PRO, false>(c, a, rows - nf, gridz, st);
+    }
+  }
+  return launch_fast_fwd_A_rows<PRO, false>(c, a, rows, gridz, st);
 }
 static int launch_fast_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
                              int mac_chain, tb200_stream st) {

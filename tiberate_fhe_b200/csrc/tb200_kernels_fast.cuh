@@ -165,11 +165,16 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
 #ifndef TB_EXT_MINB
 #define TB_EXT_MINB 3
 #endif
+#ifndef TB_F64_MINB
+#define TB_F64_MINB 4
+#endif
 // BIG: logN >= 12, where LB = 8 and the column width is 2^(12 - LA): strides, shared-memory slots and
 // load/store offsets become immediates (ncu: half of the instructions of the runtime-LB build were
 // address arithmetic).
-template <int LA, int PRO, bool BIG>
-__global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
+// F64ONLY: every limb row of the launch takes the FP64 route (launcher splits the rows as for pass B).
+template <int LA, int PRO, bool BIG, bool F64ONLY = false>
+__global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : (PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3))
+    k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int LB = BIG ? 8 : c.LB, LW = BIG ? 12 - LA : a.LW;
   const int W = 1 << LW;
@@ -188,9 +193,9 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   if constexpr (PRO == TB_FPRO_EXTEND) {
     const TbKsGroup& G = a.lv->g[gi];
     if (a.skip_own && g >= G.src_prime0 && g < G.src_prime0 + G.alpha) return;  // CTA-uniform
-    if (P.f64) {
+    if (F64ONLY || P.f64) {
       extend_prologue_f64(x, a, P, G, bt, g, c.P, tr, f0, LB, c0);
-    } else {
+    } else if constexpr (!F64ONLY) {
       switch (G.alpha) {
 #define XCASE(n) \
   case n:        \
@@ -207,14 +212,15 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
   }
   auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
   const TbTw2* tw = c.tw + ((long)g << c.logN);
-  if (P.f64) {  // integer prologues give lazy non-negative values < 2^48: exact doubles
+  if (F64ONLY || P.f64) {  // integer prologues give lazy non-negative values < 2^48: exact doubles
     if constexpr (PRO != TB_FPRO_EXTEND) tile_to_f64(x);
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.twd + ((long)g << c.logN), tb::FastF64Pol{P.qd, P.qinv}, slot);
     // stored as doubles (|x| < 2^49): pass B of the same limb takes the FP64 route as well
-  } else if (P.small) {
-    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
-  } else {
-    tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+  } else if constexpr (!F64ONLY) {
+    if (P.small)
+      tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
+    else
+      tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[(unsigned)tb::tile_x(tr, i, 0) << LB] = x[i];
@@ -223,9 +229,6 @@ __global__ void __launch_bounds__(256, PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3) 
 // forward pass B; outputs: small primes < 72q, other primes reduced to [0, 2q).
 // A CTA owns one (limb, 4096-residue tile) and can walk over `bper` consecutive batch entries (the
 // launcher uses bper = 1: see launch_fast_B for the measurement).
-#ifndef TB_F64_MINB
-#define TB_F64_MINB 4
-#endif
 // F64ONLY: every limb row of the launch takes the FP64 butterflies (the launcher splits the rows); without
 // the integer policies the kernel fits 64 registers and a fourth CTA per SM.
 template <int LB, bool F64ONLY>
