@@ -75,14 +75,17 @@ int tb200_ctx_get_twiddles(const tb200_ctx*, int inverse, int prime, int64_t* ou
 int tb200_ctx_info(const tb200_ctx*, int32_t* out /*[8]: logN,N,P,K,LA,LB,device,num_groups*/);
 /* max ciphertexts processed per internal pass by the engine layer (workspace = chunk * ~730 limb rows) */
 int tb200_ctx_set_chunk(tb200_ctx*, int chunk);
-/* 1 (default): the fused engine calls run their internal transforms on the mod-q path (Harvey/Shoup
- * butterflies, fused ModUp prologue, 128-bit key accumulation); 0: they are composed from the exact
- * op-layer kernels.  Outputs are bit-identical either way (every internal chain ends in a
- * canonicalising step); the switch exists for A/B tests and measurements. */
+/* 1 (default): the fused engine calls run their internal transforms on the mod-q path (error-free FP64
+ * products for primes below 2^42, Harvey/Shoup integer butterflies otherwise, fused ModUp prologue, key
+ * inner product without per-term reductions); 0: they are composed from the exact op-layer kernels with
+ * the reference's own lazy Montgomery butterflies.  Outputs are bit-identical either way (every internal
+ * chain ends in a canonicalising step); the switch exists for A/B tests and measurements.  The mod-q path
+ * expects key-switching key residues below 2^51 in magnitude on primes below 2^42 (the reference's keys
+ * are lazy Montgomery residues in (-2q, 2q)). */
 int tb200_ctx_set_fast(tb200_ctx*, int on);
-/* Mod-q path only: share (in eighths, 0..8) of the 40-bit-prime limbs whose butterflies run on the FP64
- * pipe (exact-integer doubles, 6 DFMA-class instructions per modular product) while the remaining limbs
- * use the integer pipes; results are bit-identical for every share. */
+/* Mod-q path only: share (in eighths, 0..8; default 8 = all) of the limbs of primes below 2^42 whose
+ * arithmetic runs on the FP64 pipe (exact-integer doubles, 6 DFMA-class instructions per modular product)
+ * while the remaining limbs use the integer pipes; results are bit-identical for every share. */
 int tb200_ctx_set_f64_share(tb200_ctx*, int eighths);
 
 /* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */
@@ -124,10 +127,15 @@ int tb200_add_many(tb200_ctx*, int pairwise, int K, int rows, int prime0, const 
 
 /* ---- op layer: NTT (ntt_radix2_cuda.cu, intt_radix2_cuda.cu, mont_used_in_ntt.cuh) ------------ */
 /* forward, in place on `rows` rows: enter != 0 -> enter_ntt_radix2 (MM by R^2 first, :98-136),
- * else ntt_radix2 (:49-96). */
+ * else ntt_radix2 (:49-96).  Outputs are the reference's lazy [0, 2q) representatives bit for bit (for
+ * primes below 2^42 and |x| < 2^50 they are computed on the FP64 pipe, other tiles on the integer one). */
 int tb200_ntt(tb200_ctx*, int rows, int batch, int prime0, const tb200_poly* a, int enter, tb200_stream);
 /* inverse, in place: mode 0 intt_radix2 (x N^-1, stays Montgomery), 1 _exit (+MR), 2 _exit_reduce
- * (+CS1, canonical), 3 _exit_reduce_signed (+centre). intt_radix2_cuda.cu:51-278. */
+ * (+CS1, canonical), 3 _exit_reduce_signed (+centre). intt_radix2_cuda.cu:51-278.
+ * Mode 2 returns canonical residues, which do not depend on the lazy representatives in between, and runs
+ * on the mod-q kernels while tb200_ctx_set_fast is on (the default).  Input domain of that route:
+ * |x| < 2^51 on primes below 2^42, (-2q, 2q) on larger primes -- every value the operators produce;
+ * tb200_ctx_set_fast(ctx, 0) selects the reference's own butterflies for anything wider. */
 int tb200_intt(tb200_ctx*, int rows, int batch, int prime0, const tb200_poly* a, int mode, tb200_stream);
 
 /* ---- op layer: fused HE kernels (he_fused_cuda.cu) ------------------------------------------- */
