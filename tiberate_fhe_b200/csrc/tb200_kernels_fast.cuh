@@ -127,6 +127,30 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
   double v[16];
   const double* le = a.lenterd + (G.lenter_off + g);
   const i64* row = a.src.row(bt, G.state_row0) + c0;
+  // software pipeline over half-tiles: while the 8 products of one half run on the FP64 pipe the 8 digit
+  // loads of the next half (same digit, or the next digit's first half) are in flight
+  auto load8 = [&](i64 (&d)[8], const i64* r, int h) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = r[(unsigned)tb::tile_x(tr, h + i, f0) << LB];
+  };
+  auto acc8 = [&](const i64 (&d)[8], int h, int k, bool wide, double C, double C30) {
+    if (wide) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double hi = tb::FastF64Pol::from_int(d[i] >> 30), lo = tb::FastF64Pol::from_int(d[i] & 0x3fffffffll);
+        const double t = __dadd_rn(pol.mulmod(hi, C30), k == 0 ? lo : pol.mulmod(lo, C));
+        v[h + i] = k == 0 ? t : __dadd_rn(v[h + i], t);
+      }
+    } else if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[h + i] = tb::FastF64Pol::from_int(d[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[h + i] = __dadd_rn(v[h + i], pol.mulmod(tb::FastF64Pol::from_int(d[i]), C));
+    }
+  };
+  i64 d0[8], d1[8];
+  load8(d0, row, 0);
   for (int k = 0; k < G.alpha; ++k) {
     const bool wide = (G.wide_mask >> k) & 1;
     double C = 1.0;
@@ -135,27 +159,11 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
       le += nP;
     }
     const double C30 = wide ? pol.mulmod(C, 1073741824.0) : 0.0;
-#pragma unroll
-    for (int h = 0; h < 16; h += 8) {
-      i64 d[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = row[(unsigned)tb::tile_x(tr, h + i, f0) << LB];
-      if (wide) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const double hi = tb::FastF64Pol::from_int(d[i] >> 30), lo = tb::FastF64Pol::from_int(d[i] & 0x3fffffffll);
-          const double t = __dadd_rn(pol.mulmod(hi, C30), k == 0 ? lo : pol.mulmod(lo, C));
-          v[h + i] = k == 0 ? t : __dadd_rn(v[h + i], t);
-        }
-      } else if (k == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[h + i] = tb::FastF64Pol::from_int(d[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[h + i] = __dadd_rn(v[h + i], pol.mulmod(tb::FastF64Pol::from_int(d[i]), C));
-      }
-    }
+    load8(d1, row, 8);
+    acc8(d0, 0, k, wide, C, C30);
     row += a.src.rs;
+    if (k + 1 < G.alpha) load8(d0, row, 0);
+    acc8(d1, 8, k, wide, C, C30);
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(v[i]);
@@ -168,12 +176,15 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
 #ifndef TB_F64_MINB
 #define TB_F64_MINB 4
 #endif
+#ifndef TB_F64A_MINB
+#define TB_F64A_MINB 3
+#endif
 // BIG: logN >= 12, where LB = 8 and the column width is 2^(12 - LA): strides, shared-memory slots and
 // load/store offsets become immediates (ncu: half of the instructions of the runtime-LB build were
 // address arithmetic).
 // F64ONLY: every limb row of the launch takes the FP64 route (launcher splits the rows as for pass B).
 template <int LA, int PRO, bool BIG, bool F64ONLY = false>
-__global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : (PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3))
+__global__ void __launch_bounds__(256, F64ONLY ? TB_F64A_MINB : (PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3))
     k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int LB = BIG ? 8 : c.LB, LW = BIG ? 12 - LA : a.LW;
