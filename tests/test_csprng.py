@@ -122,3 +122,30 @@ def test_codec_permutations_and_encode_match_reference_fixture():
     back = torch.zeros_like(dec)
     back[codec.prepost_perms(N, "cpu")[1]] = dec
     assert torch.allclose(back[: N // 2], m * 1.25, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", [0, 1], ids=["left", "right"])
+def test_gpu_constant_pool_round_trip(layout):
+    """The reference's only live unit test (tests/test_constant_mem.py:21-74) against our const_pool mirror:
+    mixed int64 / int32 entries at aligned offsets, left and right gravity, read back unchanged."""
+    import torch
+
+    from tiberate_fhe_b200.wrapper import const_pool
+
+    torch.manual_seed(42)
+    dev = torch.device("cuda:0")
+    entries = [torch.randint(1, 1_000_000, (32,), dtype=dt, device=dev)
+               for dt in (torch.int64, torch.int32, torch.int64, torch.int32, torch.int64, torch.int32, torch.int64)]
+    offsets, off = [], 0
+    for t in entries:
+        off = (off + 7) // 8 * 8
+        offsets.append(off)
+        off += t.numel() * t.element_size()
+    const_pool.upload_tensor_list(entries, offsets, layout, 0)
+    dummy = torch.empty(0, device=dev)
+    for t, o in zip(entries, offsets):
+        got = const_pool.read_constant_chunk(dummy, o, t.numel(), t.dtype, layout)
+        assert got.dtype == t.dtype and torch.equal(got, t)
+    with pytest.raises(RuntimeError):
+        const_pool.upload_tensor_list([torch.zeros(600, dtype=torch.int64, device=dev)], [0], layout, 0)

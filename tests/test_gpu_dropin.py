@@ -1,7 +1,8 @@
 """Drop-in check (BASELINE.json configs[1]): the UNMODIFIED reference CkksEngine (pip-installed
 under baseline/_ref with its own CUDA extension) runs its README scenario twice from the same CSPRNG
 state -- once on its own operators, once with tiberate_fhe_b200 installed behind
-tiberate.libs.wrapper -- and every integer tensor (keys, ciphertexts after encodecrypt, pc_mult,
+tiberate.libs.wrapper (Montgomery, NTT, fused HE, CSPRNG and constant-pool operators alike) -- and every
+integer tensor (keys, ciphertexts after encodecrypt, pc_mult,
 pc_add, cc_mult+relin, rescale, cc_add, rotate_single) must be bit-identical; decrypted values too.
 Skipped when baseline/_ref is absent (it is git-ignored; `pip install --target baseline/_ref` +
 `python baseline/ref_harness.py`).

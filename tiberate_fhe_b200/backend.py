@@ -4,12 +4,14 @@ operators on libtb200.
 The reference reaches its torch ops only through the module-level functions of
 tiberate.libs.wrapper.{mont_ops,ntt2_ops,he_ops}, looked up as module attributes at call time
 (tiberate/context/ntt_context.py:11-14,715-871; tiberate/ckks_engine.py:19), so re-pointing those
-attributes swaps the backend without touching the engine.  The reference's own
-extension stays loaded (its CSPRNG ops and constant pool are still used), which also allows
+attributes swaps the backend without touching the engine -- every operator its Python calls, the CSPRNG
+ones and the constant pool included.  The reference's own extension stays loaded, which allows
 same-process A/B comparison: `uninstall()` restores the original functions.
 """
 
 from __future__ import annotations
+
+import importlib
 
 from . import wrapper
 from .context import Tb200Context
@@ -24,6 +26,10 @@ _HOT = {
     "he_ops": ["pc_add_fused", "rescale_exact_rounding_fused", "rescale_non_exact_rounding_fused",
                "switch_key_switch_later_part_extend", "codec_rotate_make_unsigned_reduce_2q",
                "create_switcher_divide_by_p"],
+    # SURVEY 8f-1 and the constant pool: with these the reference's Python runs without calling its own
+    # extension at all
+    "csprng_ops": ["chacha20", "randint_fast", "discrete_gaussian_fast", "randint", "discrete_gaussian", "randround"],
+    "const_pool": ["upload_tensor_list", "read_constant_chunk"],
 }
 _saved = {}
 
@@ -44,7 +50,7 @@ def install_as_tiberate_backend(engine) -> list[Tb200Context]:
         wrapper.set_context(ctx)
         ctxs.append(ctx)
     for mod_name, names in _HOT.items():
-        ref_mod = getattr(ref_wrapper, mod_name)
+        ref_mod = importlib.import_module(f"tiberate.libs.wrapper.{mod_name}")
         ours = getattr(wrapper, mod_name)
         for n in names:
             _saved.setdefault((mod_name, n), getattr(ref_mod, n))
@@ -56,5 +62,5 @@ def uninstall() -> None:
     import tiberate.libs.wrapper as ref_wrapper
 
     for (mod_name, n), fn in _saved.items():
-        setattr(getattr(ref_wrapper, mod_name), n, fn)
+        setattr(importlib.import_module(f"tiberate.libs.wrapper.{mod_name}"), n, fn)
     _saved.clear()

@@ -1,5 +1,5 @@
 """Drop-in mirrors of the reference's generated op wrappers (tiberate/libs/wrapper/{mont_ops,
-ntt2_ops,he_ops}.py): same function names, argument order and meaning, same in-place / functional
+ntt2_ops,he_ops,csprng_ops,const_pool}.py): same function names, argument order and meaning, same in-place / functional
 behaviour, every tensor argument a per-device list.  They forward to libtb200 through the C ABI.
 
 The reference keeps its per-prime constants in a process-global __constant__ pool per device
@@ -32,4 +32,4 @@ def context_for(t) -> Tb200Context:
         ) from None
 
 
-from . import csprng_ops, he_ops, mont_ops, ntt2_ops  # noqa: E402,F401
+from . import const_pool, csprng_ops, he_ops, mont_ops, ntt2_ops  # noqa: E402,F401
