@@ -106,6 +106,9 @@ def cpu_oracle_hmult(steps: int, warmup: int):
     from oracle.engine import OracleEngine
 
     oracle.build()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core
+    # (only rank 0 runs it)
+    oracle.set_threads(os.cpu_count() or 1)
     q, K = preset()
     octx = OracleContext(LOGN, q, K)
     eng = OracleEngine(octx)

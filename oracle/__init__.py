@@ -65,6 +65,11 @@ _I = ctypes.c_int
 _Q = ctypes.c_int64
 
 
+def set_threads(n: int) -> None:
+    """OpenMP threads used by the C restatement (the default is libgomp's: OMP_NUM_THREADS or all cores)."""
+    lib().orc_set_threads(int(n))
+
+
 def call(name: str, *args):
     """Call a void C function; numpy arrays become pointers, ints become long."""
     conv = []

@@ -21,6 +21,18 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* thread count of the parallel loops (bench.py's CPU arm: torchrun caps OMP_NUM_THREADS at 1) */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 typedef int64_t i64;
 typedef uint64_t u64;
