@@ -376,6 +376,14 @@ def check_engine(s: Setup, level: int, batch=None, ops=("rescale", "keyswitch", 
             w = each(lambda a, b: eng.cc_mult(a, b, s.evk, level, pre_rescale=pre)[0])
             eq(h, o0, w[0], f"cc_mult+relin level {level} pre_rescale={pre} c0")
             eq(h, o1, w[1], f"cc_mult+relin level {level} pre_rescale={pre} c1")
+        # squaring: the same tensors as both operands (two transforms instead of four)
+        pre = can_rescale
+        sh = shp1 if pre else shp
+        o0, o1 = h.zeros(*sh), h.zeros(*sh)
+        ctx.cc_mult_relin(level, d1[0], d1[1], d1[0], d1[1], s.evk_d, o0, o1, pre)
+        w = each(lambda a, b: eng.cc_mult(a, a, s.evk, level, pre_rescale=pre)[0])
+        eq(h, o0, w[0], f"cc_mult+relin of a ciphertext with itself, level {level} c0")
+        eq(h, o1, w[1], f"cc_mult+relin of a ciphertext with itself, level {level} c1")
     if "triplet" in ops:
         pre = can_rescale
         sh = shp1 if pre else shp

@@ -1310,7 +1310,11 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
   const int L = c->num_ord - lvl;
   const size_t pe = (size_t)nb * L * N;
   TbView in[4] = {a0, a1, b0, b1};
-  for (int i = 0; i < 4; ++i) {
+  // squaring (both operands are the same tensors): the transformed operands are identical, so two of the
+  // four rescale + forward transforms suffice and the tensor product reads them twice
+  const bool square = a0.p == b0.p && a1.p == b1.p && a0.bs == b0.bs && a1.bs == b1.bs && a0.rs == b0.rs &&
+                      a1.rs == b1.rs;
+  for (int i = 0; i < (square ? 2 : 4); ++i) {
     TbView xi = dense(x + i * pe, L, N);
     if (fast) {
       int rc = fast_forward_enter(c, in[i], xi, L, nb, lvl, pre_rescale ? level : -1, st);
@@ -1325,7 +1329,8 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
     }
   }
   LAUNCH(k_tensor, grid_pw(c, L, nb, 2), dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), dense(x, L, N),
-         dense(x + pe, L, N), dense(x + 2 * pe, L, N), dense(x + 3 * pe, L, N), d0, d1, d2, lvl, N);
+         dense(x + pe, L, N), dense(x + (square ? 0 : 2) * pe, L, N), dense(x + (square ? 1 : 3) * pe, L, N), d0, d1,
+         d2, lvl, N);
   return 0;
 }
 
