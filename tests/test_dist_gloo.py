@@ -100,6 +100,18 @@ def _sharded_ks_worker(rank, world, port, seed):
             ks(level, a_loc, key, o0, o1)
             rows = [g - level for g in ctx.local_rows(level)]
             assert np.array_equal(o0.numpy(), want0[rows]) and np.array_equal(o1.numpy(), want1[rows]), (rank, level)
+        # limb-sharded rescale: the owner of the dropped prime broadcasts it, every rank rescales its rows
+        from tiberate_fhe_b200.dist import LimbShardedRescale
+
+        rs = LimbShardedRescale(ctx)
+        for level in (0, 1, 3):
+            lp = octx.level_primes(level, False)
+            ct = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+            want = eng.rescale(ct, level)
+            loc = [shard_rows(torch.from_numpy(x), ctx, level) for x in ct]
+            o0, o1 = rs(level, loc[0], loc[1])
+            rows = [g - level - 1 for g in ctx.local_rows(level + 1)]
+            assert np.array_equal(o0.numpy(), want[0][rows]) and np.array_equal(o1.numpy(), want[1][rows]), (rank, level)
         ctx.close()
     finally:
         dist.destroy_process_group()

@@ -57,6 +57,19 @@ def _worker(rank, world, port):
             rows = [g - level for g in ctx.local_rows(level)]
             assert np.array_equal(o0.cpu().numpy(), want0[rows]), (rank, level)
             assert np.array_equal(o1.cpu().numpy(), want1[rows]), (rank, level)
+        # limb-sharded rescale: one NCCL broadcast of the dropped limb, then local kernels
+        from tiberate_fhe_b200.dist import LimbShardedRescale
+
+        rs = LimbShardedRescale(ctx)
+        for level in (0, 2, 5):
+            lp = octx.level_primes(level, False)
+            ct = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+            want = eng.rescale(ct, level)
+            loc = [shard_rows(torch.from_numpy(x), ctx, level).to(dev) for x in ct]
+            r0, r1 = rs(level, loc[0], loc[1])
+            rows = [g - level - 1 for g in ctx.local_rows(level + 1)]
+            assert np.array_equal(r0.cpu().numpy(), want[0][rows]), (rank, level)
+            assert np.array_equal(r1.cpu().numpy(), want[1][rows]), (rank, level)
         ctx.close()
 
         # 2. logN17 (79 primes, 13 digit groups): sharded result == unsharded result of rank 0

@@ -105,6 +105,50 @@ class LimbShardedKeySwitch:
         return out0, out1
 
 
+class LimbShardedRescale:
+    """Rescale of a limb-sharded ciphertext (tiberate/ckks_engine.py:1520-1618; the reference ships the
+    dropped limb to the other devices with `tensor.to(device)`, :1560-1575).
+
+    The rank that owns prime `level` broadcasts the dropped limb of both polynomials (2 N int64 -- the
+    one exchange of this operation), then every rank rescales the limbs it keeps with the op-layer kernel
+    (tb200_rescale_rows).  Returns this rank's rows at level + 1 (fresh tensors)."""
+
+    def __init__(self, ctx, group=None):
+        import torch.distributed as dist
+
+        self.ctx, self.group = ctx, group
+        self.world = dist.get_world_size(group)
+        if ctx.world != self.world or ctx.rank != dist.get_rank(group):
+            raise ValueError("context rank/world must match the process group")
+
+    def __call__(self, level: int, c0_local, c1_local, exact: bool = True):
+        import torch
+        import torch.distributed as dist
+
+        ctx = self.ctx
+        ids = ctx.local_rows(level)
+        owner = level in ids
+        drop = torch.zeros(2, ctx.N, dtype=torch.int64, device=c0_local.device)
+        if owner:  # the dropped prime is the smallest alive id: local row 0
+            drop[0].copy_(c0_local[0])
+            drop[1].copy_(c1_local[0])
+        if self.world > 1:
+            who = torch.tensor([ctx.rank if owner else -1], dtype=torch.int64, device=c0_local.device)
+            dist.all_reduce(who, op=dist.ReduceOp.MAX, group=self.group)
+            dist.broadcast(drop, src=int(who.item()), group=self.group)
+        kept = [g for g in ids if g > level]
+        outs = []
+        for i, c in enumerate((c0_local, c1_local)):
+            out = (c[1:] if owner else c).clone()
+            if kept:
+                ql, R = ctx.q_global[level], 1 << 62
+                scales = torch.tensor([(pow(ql, -1, ctx.q_global[g]) * R) % ctx.q_global[g] for g in kept],
+                                      dtype=torch.int64, device=c.device)
+                ctx.rescale_rows(out, ctx.local_prime_ids.index(kept[0]), scales, drop[i], ql // 2, exact)
+            outs.append(out)
+        return outs[0], outs[1]
+
+
 def shard_rows(t, ctx, level: int, with_special: bool = False):
     """Rows of a full [L(+K), N] level-`level` tensor that live on ctx's rank (a copy, contiguous)."""
     rows = [g - level for g in ctx.local_rows(level)]
