@@ -172,6 +172,9 @@ def run_ours(args):
     ctx.set_chunk(args.chunk)
     if args.f64_share is not None:
         ctx.set_f64_share(args.f64_share)
+    for kv in args.tune or []:
+        k, v = kv.split("=")
+        ctx.set_tuning(int(k), int(v))
     N, P, no = ctx.N, ctx.P, ctx.num_ordinary
     L = no - 1
     B = args.batch
@@ -451,6 +454,7 @@ def main():
     ap.add_argument("--no-reference-ext", action="store_true")
     ap.add_argument("--f64-share", type=int, default=None,
                     help="eighths of the 40-bit-prime limbs transformed on the FP64 pipe (default: library default)")
+    ap.add_argument("--tune", action="append", help="knob=value of tb200_ctx_set_tuning (A/B measurements)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the secondary rotate / NTT figures and the reference ext")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -87,6 +87,17 @@ int tb200_ctx_set_fast(tb200_ctx*, int on);
  * arithmetic runs on the FP64 pipe (exact-integer doubles, 6 DFMA-class instructions per modular product)
  * while the remaining limbs use the integer pipes; results are bit-identical for every share. */
 int tb200_ctx_set_f64_share(tb200_ctx*, int eighths);
+/* Mod-q path only: scheduling knobs for A/B measurements; results are bit-identical for every setting.
+ *   TB200_TUNE_FUSED_CORE (default 1): FP64 limbs run pass B of every digit group, the key inner product
+ *     and inverse pass B as one kernel (no HBM round trip of the transformed extensions); 0: three kernels.
+ *   TB200_TUNE_SIDE_ROWS (default 0: measured no gain, the first kernel fills the GPU): inside a key switch
+ *     the launches over the 60-bit limb rows (integer pipes) are forked onto a library-owned stream and
+ *     joined again, beside the launches over the FP64 limb rows; 0: one stream.
+ *   TB200_TUNE_FUSED_MODDOWN (default 0: measured 63 us against 36 + 20 us separately, B200 logN16): ModDown and the relinearisation / switch-key tail run inside the
+ *     exit of inverse pass A of the ordinary limbs (after the special limbs were transformed and
+ *     chain-reduced); 0: separate kernels over the coefficient-domain sums. */
+enum tb200_tuning { TB200_TUNE_FUSED_CORE = 0, TB200_TUNE_SIDE_ROWS = 1, TB200_TUNE_FUSED_MODDOWN = 2 };
+int tb200_ctx_set_tuning(tb200_ctx*, int knob, int value);
 
 /* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */
 enum tb200_pw_op {

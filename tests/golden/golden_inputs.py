@@ -49,5 +49,5 @@ def record(a: np.ndarray) -> dict:
 
 
 # the cases: name -> (levels to run at); kept identical in generator and checkers
-LEVEL_CASES = {14: [0, 3, 6], 15: [0, 1, 8, 15]}
+LEVEL_CASES = {14: [0, 3, 6], 15: [0, 1, 8, 15], 16: [0, 17, 33]}
 ROT_DELTA = 5

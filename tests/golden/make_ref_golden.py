@@ -24,7 +24,7 @@ sys.path.insert(0, HERE)
 import golden_inputs as gi  # noqa: E402
 
 
-def main(outdir: str, logNs=(14, 15)):
+def main(outdir: str, logNs=(14, 15, 16)):
     import torch
 
     from baseline import ref_harness
@@ -149,4 +149,5 @@ def main(outdir: str, logNs=(14, 15)):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"),
+         tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (14, 15, 16))

@@ -310,13 +310,17 @@ def check_he_ops(s: Setup, level=0):
 
 # Internal-transform modes of the fused engine calls, all bit-identical by contract:
 # (mod-q path?, eighths of the 40-bit limbs on the FP64 pipe)
-ENGINE_MODES = ((False, 0), (True, 0), (True, 3), (True, 8))  # the default last
+# optional third entry: 0 = the key-switch core as three kernels instead of the fused one
+# and fourth: 1 = ModDown inside the inverse pass-A exit instead of separate kernels
+ENGINE_MODES = ((False, 0), (True, 0), (True, 3), (True, 8, 0, 1), (True, 8))  # the default last
 
 
 def set_mode(s: "Setup", mode):
-    fast, share = mode
+    fast, share = mode[0], mode[1]
     s.ctx.set_fast(fast)
     s.ctx.set_f64_share(share)
+    s.ctx.set_tuning(s.ctx.TUNE_FUSED_CORE, mode[2] if len(mode) > 2 else 1)
+    s.ctx.set_tuning(s.ctx.TUNE_FUSED_MODDOWN, mode[3] if len(mode) > 3 else 0)
 
 
 def check_engine(s: Setup, level: int, batch=None, ops=("rescale", "keyswitch", "switch_key", "rotate", "cc_mult",

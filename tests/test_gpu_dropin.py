@@ -26,7 +26,7 @@ def _flatten(x, out):
     return out
 
 
-@pytest.mark.parametrize("preset", ["logN14", "logN15"])
+@pytest.mark.parametrize("preset", ["logN14", "logN15", "logN16"])
 def test_reference_engine_on_tb200_backend_is_bit_identical(preset):
     import torch
 

@@ -55,7 +55,7 @@ def engine_logN(engine):
     return engine.ckksCfg.logN if hasattr(engine, "ckksCfg") else engine.logN
 
 
-@pytest.mark.parametrize("preset", ["logN14", "logN15"])
+@pytest.mark.parametrize("preset", ["logN14", "logN15", "logN16"])
 def test_keys_and_ciphertexts_match_the_reference_engine(preset):
     import torch
 
@@ -87,7 +87,7 @@ def test_keys_and_ciphertexts_match_the_reference_engine(preset):
     assert torch.equal(ref.rng.states[0], ours.rng.states[0]), "CSPRNG consumption differs"
 
 
-@pytest.mark.parametrize("preset", ["logN14", "logN15"])
+@pytest.mark.parametrize("preset", ["logN14", "logN15", "logN16"])
 def test_readme_scenario_matches_the_reference_engine(preset):
     """encodecrypt -> pc_mult -> pc_add -> cc_mult -> rescale -> cc_add -> rotate_single ->
     decryptcode, float messages in, float messages out, on the reference engine (own extension) and on

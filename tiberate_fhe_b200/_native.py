@@ -53,6 +53,7 @@ SIGNATURES = {
     "tb200_ctx_set_chunk": (_i, [_vp, _i]),
     "tb200_ctx_set_fast": (_i, [_vp, _i]),
     "tb200_ctx_set_f64_share": (_i, [_vp, _i]),
+    "tb200_ctx_set_tuning": (_i, [_vp, _i, _i]),
     "tb200_pointwise": (_i, [_vp, _i, _i, _i, _i, PP, PP, _vp, C.POINTER(ExplicitConsts), PP, _vp]),
     "tb200_add_many": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tb200_ntt": (_i, [_vp, _i, _i, _i, PP, _i, _vp]),

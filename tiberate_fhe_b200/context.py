@@ -172,6 +172,12 @@ class Tb200Context:
         """Share (0..8 eighths) of the small-prime limbs transformed on the FP64 pipe (mod-q path)."""
         self.lib.check(self.lib.tb200_ctx_set_f64_share(self.h, int(eighths)), "set_f64_share")
 
+    TUNE_FUSED_CORE, TUNE_SIDE_ROWS, TUNE_FUSED_MODDOWN = 0, 1, 2
+
+    def set_tuning(self, knob: int, value: int):
+        """Scheduling knobs of the mod-q path (include/tb200.h: enum tb200_tuning); results never change."""
+        self.lib.check(self.lib.tb200_ctx_set_tuning(self.h, int(knob), int(value)), "set_tuning")
+
     # ---- level helpers -------------------------------------------------------------------
     def rows_at(self, level: int, with_special: bool = False) -> int:
         return (self.P if with_special else self.num_ordinary) - level
@@ -180,8 +186,9 @@ class Tb200Context:
         """a tensor of `rows` rows called with sp_prime_len addresses the
         constant pool right-aligned: row i -> prime P - rows - sp_prime_len + i."""
         p0 = self.P - rows - sp_prime_len
-        if p0 < 0:
-            raise Tb200Error(f"{rows} rows with sp_prime_len={sp_prime_len} exceed the {self.P} primes")
+        if p0 < self.P - 64:  # the reference would read another constant's region of its pool
+            raise Tb200Error(f"{rows} rows with sp_prime_len={sp_prime_len} exceed the reference's 64-slot pool")
+        # p0 < 0: the leading rows use the zero padding of the pool (pointwise ops only; the C side checks)
         return p0
 
     # ---- op layer ------------------------------------------------------------------------

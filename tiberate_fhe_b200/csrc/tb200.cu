@@ -59,6 +59,13 @@ static std::vector<ProfRec> g_prof;
     PROF_END(stream)                                                     \
     g_launches.fetch_add(1, std::memory_order_relaxed);                  \
   } while (0)
+#define LAUNCH_DYN(kname, kernel, grid, block, smem, stream, ...)                       \
+  do {                                                                                  \
+    PROF_BEGIN(kname, stream)                                                           \
+    TB_LAUNCH_DYN(kernel, grid, block, smem, (cudaStream_t)(stream), __VA_ARGS__);      \
+    PROF_END(stream)                                                                    \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+  } while (0)
 #define POST()                                                                     \
   do {                                                                             \
     cudaError_t e_ = cudaPeekAtLastError();                                        \
@@ -136,6 +143,9 @@ extern "C" void tb200_ctx_destroy(tb200_ctx* c) {
   cudaFree(c->d_cP);
   cudaFree(c->d_bn);
   cudaFree(c->ws);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
@@ -510,6 +520,22 @@ extern "C" int tb200_ctx_set_f64_share(tb200_ctx* c, int eighths) {
   return 0;
 }
 
+extern "C" int tb200_ctx_set_tuning(tb200_ctx* c, int knob, int value) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  switch (knob) {
+    case TB200_TUNE_FUSED_CORE:
+      c->fused_core = value != 0;
+      return 0;
+    case TB200_TUNE_SIDE_ROWS:
+      c->side_rows = value != 0;
+      return 0;
+    case TB200_TUNE_FUSED_MODDOWN:
+      c->fused_moddown = value != 0;
+      return 0;
+  }
+  return fail(TB200_EINVAL, "unknown tuning knob %d", knob);
+}
+
 static int ws_reserve(tb200_ctx* c, size_t elems) {
   if (elems <= c->ws_elems) return 0;
   // grow-only; the previous buffer may still be in use by queued kernels of the caller's stream
@@ -582,7 +608,9 @@ extern "C" int tb200_pointwise(tb200_ctx* c, int op, int rows, int batch, int pr
   const bool has_b = op <= 4 || op == 13;
   const bool needs_scal = op == 5 || op == 14;
   const bool explicit_c = ec && (ec->ql || ec->two_q);
-  if (!explicit_c) CHECK_ROWS(prime0, rows);
+  // prime0 in [P - 64, 0): the leading rows address the zero padding of the reference's 64-slot pool
+  if (!explicit_c && !(prime0 < 0 && prime0 >= c->P - 64 && rows >= 1 && prime0 + rows <= c->P))
+    CHECK_ROWS(prime0, rows);
   if (rows < 1) return fail(TB200_EINVAL, "rows must be >= 1");
   {
     int rc = check_poly(c, a, "a", op == TB200_TILE_UNSIGNED);
@@ -810,15 +838,22 @@ static int launch_fast_fwd_A(const tb200_ctx* c, TbFwdAArgs a, int rows, int gri
   return launch_fast_fwd_A_rows<PRO, false>(c, a, rows, gridz, st);
 }
 static int launch_fast_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
-                             int mac_chain, tb200_stream st) {
+                             int mac_chain, tb200_stream st, const TbMdArgs* md = nullptr) {
   const int lw = ntt_lw(c);
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
   const bool big = c->LB == 8 && lw == 12 - c->LA;
+  TbMdArgs m0;
+  memset(&m0, 0, sizeof(m0));
   switch (c->LA + (big ? 100 : 0)) {
-#define ACASE(n, B)                                                                            \
-  case n + (B ? 100 : 0): {                                                                    \
-    auto kfn = k_fast_inv_A<n, B>;                                                             \
-    LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw, mac_chain); \
+#define ACASE(n, B)                                                                                       \
+  case n + (B ? 100 : 0): {                                                                               \
+    if (md) {                                                                                             \
+      auto kfn = k_fast_inv_A<n, B, true>;                                                                \
+      LAUNCHN("k_fast_inv_A_moddown", kfn, grid, block, st, c->devf(), src, dst, prime0, lw, mac_chain, *md); \
+    } else {                                                                                              \
+      auto kfn = k_fast_inv_A<n, B, false>;                                                               \
+      LAUNCHN("k_fast_inv_A", kfn, grid, block, st, c->devf(), src, dst, prime0, lw, mac_chain, m0);      \
+    }                                                                                                     \
   } break;
     ACASE(4, false) ACASE(5, false) ACASE(6, false)
     ACASE(4, true) ACASE(5, true) ACASE(6, true) ACASE(7, true) ACASE(8, true) ACASE(9, true)
@@ -888,6 +923,42 @@ static int launch_fast_B(const tb200_ctx* c, bool inverse, TbView src, TbView ds
     rc = launch_fast_B_rows(c, inverse, false, rows_from(src, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st,
                             in_mode, skip_lv, dbl_out);
   return rc;
+}
+// Fork / join of the library-owned side stream around a section of the caller's stream (event pair; both are
+// ordinary stream operations, so the section stays capturable in a CUDA graph).
+static int side_stream_fork(tb200_ctx* c, tb200_stream st) {
+  if (!c->side) {
+    CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(c->ev_fork, (cudaStream_t)st));
+  CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  return 0;
+}
+static int side_stream_join(tb200_ctx* c, tb200_stream st) {
+  CK(cudaEventRecord(c->ev_join, c->side));
+  CK(cudaStreamWaitEvent((cudaStream_t)st, c->ev_join, 0));
+  return 0;
+}
+// pass B of every digit group + key inner product + inverse pass B' for `rows` FP64 limb rows
+static int launch_ks_core(const tb200_ctx* c, const TbKsCoreArgs& a, int rows, tb200_stream st) {
+  const int te = c->N < TB_TILE ? c->N : TB_TILE;
+  const dim3 grid((unsigned)((c->N / te) * a.nb), (unsigned)rows, 1u), block((unsigned)(te / 16));
+  const size_t smem = (size_t)2 * te * 8;
+  switch (c->LB) {
+#define KCASE(n)                                                                                         \
+  case n: {                                                                                              \
+    auto kfn = k_fast_ks_core_f64<n>;                                                                    \
+    TB_SET_MAX_DYN_SMEM(kfn, TB_KSCORE_STAGE_BYTES);                                                     \
+    LAUNCH_DYN("k_fast_ks_core", kfn, grid, block, smem, st, c->devf(), a);                              \
+  } break;
+    KCASE(4) KCASE(5) KCASE(6) KCASE(7) KCASE(8)
+#undef KCASE
+    default:
+      return fail(TB200_EINVAL, "unsupported LB %d", c->LB);
+  }
+  return 0;
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
 static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
@@ -1089,7 +1160,10 @@ static int ks_digits(tb200_ctx* c, int level, int nb, TbView a, TbView state, tb
 struct TbRelinExtra {
   bool own_prefilled;
   const i64 *nadd0, *nadd1;
+  const i64* own_ntt;  // NTT-domain key-switch input (dense [nb][L][N]): the fused core reads the own limbs from it
 };
+// rows [0, nf) of a key switch at this level go through the fused core kernel
+static int ks_core_rows(const tb200_ctx* c, int p0, int E) { return (c->fast && c->fused_core) ? f64_prefix(c, p0, E) : 0; }
 static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskDev& key, TbView add0, TbView add1,
                      TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, const TbRelinExtra* ex = nullptr) {
   const bool own_prefilled = ex && ex->own_prefilled;
@@ -1113,17 +1187,81 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     fa.prime0 = p0;
     fa.ngroups = ng;
     fa.skip_own = own_prefilled ? 1 : 0;
-    if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) return rc;
-    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, st, 0,
-                            own_prefilled ? dlv : nullptr, 1)))
+    // FP64 limbs: pass B of every group + key inner product + inverse pass B' in one kernel (tb200_ks_core.cuh);
+    // the remaining limbs (60-bit base / special primes) take the three separate kernels on their rows --
+    // on a forked stream: they load the integer pipes, the FP64 rows the FP64 pipe.
+    const int nf = ks_core_rows(c, p0, E);
+    const bool split_a = c->LB == 8 && ntt_lw(c) == 12 - c->LA && nf > 0;  // FP64-only pass A instantiation exists
+    tb200_stream sst = st;
+    if (nf > 0 && nf < E && split_a && c->side_rows && !g_prof_on) {
+      if ((rc = side_stream_fork(c, st))) return rc;
+      sst = (tb200_stream)c->side;
+    }
+    if (split_a) {
+      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_EXTEND, true>(c, fa, nf, nb * ng, st))) return rc;
+      if (nf < E) {
+        TbFwdAArgs fb = fa;
+        fb.prime0 += nf;
+        fb.dst = rows_from(fb.dst, nf);
+        if ((rc = launch_fast_fwd_A_rows<TB_FPRO_EXTEND, false>(c, fb, E - nf, nb * ng, sst))) return rc;
+      }
+    } else if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) {
       return rc;
-    // key inner product, 128-bit accumulation over the groups
-    LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u),
-           dim3(N / 2 < 256 ? N / 2 : 256), st, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb,
-           ex ? ex->nadd0 : (const i64*)nullptr, ex ? ex->nadd1 : (const i64*)nullptr, (const i64*)c->d_cP);
+    }
+    if (nf > 0) {
+      TbKsCoreArgs ka;
+      memset(&ka, 0, sizeof(ka));
+      ka.lv = dlv;
+      ka.key = key;
+      ka.ext = ext;
+      ka.acc = acc;
+      ka.nadd0 = ex ? ex->nadd0 : nullptr;
+      ka.nadd1 = ex ? ex->nadd1 : nullptr;
+      ka.p0 = p0;
+      ka.row0 = 0;
+      ka.N = N;
+      ka.rowsE = E;
+      ka.nb = nb;
+      ka.skip_own = own_prefilled ? 1 : 0;
+      ka.own = ex ? ex->own_ntt : nullptr;
+      ka.pr = c->d_primes;
+      if ((rc = launch_ks_core(c, ka, nf, st))) return rc;
+    }
+    if (nf < E) {
+      const TbView er = rows_from(dense(ext, E, N), nf);
+      if ((rc = launch_fast_B(c, false, er, er, E - nf, nb * ng, p0 + nf, sst, 0, own_prefilled ? dlv : nullptr, 1)))
+        return rc;
+      // key inner product, 128-bit accumulation over the groups
+      LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)(E - nf), 1u),
+             dim3(N / 2 < 256 ? N / 2 : 256), sst, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb,
+             ex ? ex->nadd0 : (const i64*)nullptr, ex ? ex->nadd1 : (const i64*)nullptr, (const i64*)c->d_cP, nf);
+      const TbView ar = rows_from(dense(acc, E, N), nf);
+      if ((rc = launch_fast_B(c, true, ar, ar, E - nf, nb * 2, p0 + nf, sst, TB_INV_IN_DOUBLE))) return rc;
+    }
+    if (sst != st && (rc = side_stream_join(c, st))) return rc;
     if (ex && ex->nadd0) tail = 0;  // already inside the sums
-    // back to coefficients, canonical
-    if ((rc = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, st, 1))) return rc;
+    if (c->fused_moddown) {
+      // special limbs first (inverse pass A' + exit, then the exact chain-backward step), then the ordinary
+      // limbs with ModDown and the tail fused into the exit: they go straight to the output rows
+      const TbView sp = rows_from(dense(acc, E, N), L);
+      if ((rc = launch_fast_inv_A(c, sp, sp, c->K, nb * 2, p0 + L, 1, st))) return rc;
+      LAUNCH(k_chain_backward, grid_pw(c, 1, nb * 2, 1), dim3(256), st, c->dev(), sp, (const i64*)c->d_pir_sp, c->K,
+             c->num_ord, c->N);
+      TbMdArgs md;
+      memset(&md, 0, sizeof(md));
+      md.p = acc + (size_t)L * N;
+      md.pbs = (long)E * N;
+      md.bn = c->d_bn;
+      md.add0 = add0;
+      md.add1 = add1;
+      md.out0 = out0;
+      md.out1 = out1;
+      md.K = c->K;
+      md.tail = tail;
+      return launch_fast_inv_A(c, dense(acc, E, N), dense(acc, E, N), L, nb * 2, p0, 1, st, &md);
+    }
+    // inverse pass A' + exit: back to coefficients, canonical
+    if ((rc = launch_fast_inv_A(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, 1, st))) return rc;
   } else {
     LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
            dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, state, ext, p0, N, E);
@@ -1363,22 +1501,28 @@ extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const t
 }
 
 // relinearize one chunk: d (dense [3][nb][L][N], NTT+Montgomery, destroyed) -> out
-static int relin_chunk(tb200_ctx* c, int lvl, int nb, i64* d, const TbKskDev& key, TbView out0, TbView out1, i64* ksws,
-                       tb200_stream st) {
+// dcoef: scratch of nb * L * N words for the coefficient form of d2 (may not alias d)
+static int relin_chunk(tb200_ctx* c, int lvl, int nb, i64* d, i64* dcoef, const TbKskDev& key, TbView out0, TbView out1,
+                       i64* ksws, tb200_stream st) {
   const int N = c->N, L = c->num_ord - lvl;
   const size_t pe = (size_t)nb * L * N;
   const bool reuse = c->fast && c->world == 1;
-  if (reuse) {  // NTT-domain d2 = forward transform of every group's extension at its own limbs (k_fast_own_fill)
-    i64* ext = ksws + (size_t)nb * c->ks[lvl].state_rows * N;  // where keyswitch_chunk / ks_finish put it
-    LAUNCH(k_fast_own_fill, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)L, (unsigned)nb),
-           dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), c->devf(), (const TbKsLevel*)(c->d_ks + lvl),
-           dense(d + 2 * pe, L, N), ext, lvl, N, L + c->K);
-  }
-  if (reuse) {  // d0 / d1 stay in the NTT domain and enter the key inner product (k_fast_mac)
-    int rc = fast_inverse_exit(c, dense(d + 2 * pe, L, N), dense(d + 2 * pe, L, N), L, nb, lvl, st);
+  if (reuse) {
+    // NTT-domain d2 = forward transform of every group's extension at its own limbs: the fused core reads
+    // those limbs from d2 itself, the rows outside it get them from k_fast_own_fill
+    const int nf = ks_core_rows(c, lvl, L + c->K) < L ? ks_core_rows(c, lvl, L + c->K) : L;
+    if (nf < L) {
+      i64* ext = ksws + (size_t)nb * c->ks[lvl].state_rows * N;  // where keyswitch_chunk / ks_finish put it
+      LAUNCH(k_fast_own_fill, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)(L - nf), (unsigned)nb),
+             dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), c->devf(), (const TbKsLevel*)(c->d_ks + lvl),
+             dense(d + 2 * pe, L, N), ext, lvl, N, L + c->K, nf);
+    }
+    // d2 back to coefficients, out of place (dcoef): its NTT form stays for the core; d0 / d1 stay in the NTT
+    // domain and enter the key inner product
+    int rc = fast_inverse_exit(c, dense(d + 2 * pe, L, N), dense(dcoef, L, N), L, nb, lvl, st);
     if (rc) return rc;
-    const TbRelinExtra ex = {true, d, d + pe};
-    return keyswitch_chunk(c, lvl, nb, dense(d + 2 * pe, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1,
+    const TbRelinExtra ex = {true, d, d + pe, d + 2 * pe};
+    return keyswitch_chunk(c, lvl, nb, dense(dcoef, L, N), key, dense(d, L, N), dense(d + pe, L, N), out0, out1,
                            1, ksws, st, &ex);
   }
   int rc = c->fast ? fast_inverse_exit(c, dense(d, L, N), dense(d, L, N), L, 3 * nb, lvl, st)
@@ -1404,7 +1548,7 @@ extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200
   CK(cudaSetDevice(c->device));
   const int N = c->N, L = c->num_ord - level;
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, (3 * (size_t)L * N + ks_ws_elems(c, level)) * ch))) return rc;
+  if ((rc = ws_reserve(c, (4 * (size_t)L * N + ks_ws_elems(c, level)) * ch))) return rc;
   for (int b = 0; b < batch; b += ch) {
     const int nb = batch - b < ch ? batch - b : ch;
     const size_t pe = (size_t)nb * L * N;
@@ -1420,7 +1564,7 @@ extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200
       g.N = N;
       launch_pw<15>(c, g, L, nb, st);
     }
-    rc = relin_chunk(c, level, nb, d, key, shift(view(out0), b), shift(view(out1), b), d + 3 * pe, st);
+    rc = relin_chunk(c, level, nb, d, d + 3 * pe, key, shift(view(out0), b), shift(view(out1), b), d + 4 * pe, st);
     if (rc) return rc;
   }
   POST();
@@ -1457,7 +1601,7 @@ extern "C" int tb200_cc_mult_relin(tb200_ctx* c, int level, int batch, const tb2
     rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
                     pre_rescale, x, dense(d, L, N), dense(d + pe, L, N), dense(d + 2 * pe, L, N), c->fast != 0, st);
     if (rc) return rc;
-    rc = relin_chunk(c, lvl, nb, d, key, shift(view(out0), b), shift(view(out1), b), ksws, st);
+    rc = relin_chunk(c, lvl, nb, d, x, key, shift(view(out0), b), shift(view(out1), b), ksws, st);  // x is free again
     if (rc) return rc;
   }
   POST();

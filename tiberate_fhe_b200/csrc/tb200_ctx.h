@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "tb200_kernels_fast.cuh"
+#include "tb200_ks_core.cuh"
 
 typedef __int128 i128;
 typedef unsigned __int128 u128;
@@ -84,6 +84,11 @@ struct tb200_ctx {
   TbKsLevel* d_ks = nullptr; // [num_ord]
   // fast (mod-q) path tables
   int fast = 1;
+  int fused_core = 1;        // FP64 limbs: pass B + key inner product + inverse pass B' in one kernel
+  int fused_moddown = 0;     // ModDown + tail inside the exit of inverse pass A' of the ordinary limbs (measured slower)
+  int side_rows = 0;         // the 60-bit limb rows of a key switch run on a forked stream beside the FP64 rows
+  cudaStream_t side = nullptr;            // created on first use (device of the context)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int f64_eighths = 8;       // share (in eighths) of the small-prime limbs whose butterflies use the FP64 pipe
   std::vector<TbFastPrime> fps;
   TbFastPrime* d_fp = nullptr;

@@ -57,8 +57,25 @@ struct TbPwArgs {
   int prime0, N;
 };
 
+// Slots of the reference's right-aligned 64-entry constant pool below its first prime are zero padding
+// (constant_mem_context.py:100-123).  A call whose rows + sp_prime_len exceed the number of primes reads them
+// (decrypt_triplet's s2 = mont_mult(sk, sk) does, ckks_engine.py:669, at levels < K), and with q = k = 0 the
+// reference's product degenerates to floor(a b / 2^62) (mont_scalar_kernel.cuh:9-58 with s = 0) -- without
+// the "+ [low bits != 0]" carry that the closed form adds for a real prime.
+__device__ __forceinline__ i64 tb_mm_zero_slot(i64 a, i64 b) {
+  const u64 lo = (u64)a * (u64)b;
+  return (i64)(((u64)__mul64hi(a, b) << 2) | (lo >> 62));
+}
+
 template <int OP>
 __device__ __forceinline__ i64 pw_apply(i64 a, i64 b, i64 s, i64 q, i64 q2, u64 q4, u64 k, i64 Rs, i64 Rss) {
+  if (q4 == 0) {  // zero-padding slot of the reference's pool: every constant is 0
+    if constexpr (OP == 0) return tb_mm_zero_slot(a, b);
+    if constexpr (OP == 5 || OP == 14) return tb_mm_zero_slot(a, s);
+    if constexpr (OP == 6 || OP == 7) return 0;
+    if constexpr (OP == 8) return a >> 62;
+    if constexpr (OP == 13) return b >> 62;
+  }
   if constexpr (OP == 0) return tb_mm_ss(a, b, q4, k);
   if constexpr (OP == 1) return tb_add(a, b, q2);
   if constexpr (OP == 2) return tb_sub(a, b, q2);
@@ -94,6 +111,9 @@ __global__ void __launch_bounds__(256) k_pointwise(TbDev c, TbPwArgs g) {
     }
     q4 = (u64)q << 2;
     k = (g.kl != nullptr) ? (u64)(g.kl[r] + (g.kh[r] << 31)) : 0ull;
+  } else if (g.prime0 + r < 0) {
+    q = q2 = 0;
+    q4 = k = 0;
   } else {
     const TbPrime& P = c.pr[g.prime0 + r];
     q = P.q;

@@ -360,18 +360,63 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_inv_B(T
   }
 }
 
+// ModDown fused into the exit of inverse pass A' (MD instantiation): the ordinary limbs of the two key sums
+// never return to HBM in coefficient form.  The special limbs were transformed and chain-reduced before
+// (k_chain_backward, exact); here y = c B_{K-1} - sum_k p_k B_k mod q (he_fused_cuda.cu:471-519 expanded, see
+// k_fast_divide_by_p) + the relinearisation / switch-key tail, written to the caller's output rows.
+struct TbMdArgs {
+  const i64* p;       // special limbs: element (z, k, j) at p + z * pbs + k * N + j   (z = ciphertext * 2 + half)
+  long pbs;
+  const u64* bn;      // [(K+1)][P][2]
+  TbView add0, add1, out0, out1;
+  int K, tail;        // tail as in ks_finish
+};
+__device__ __forceinline__ i64 tb_moddown_exit(i64 cv, const TbFastPrime& P, const u64* b, int nP, const TbMdArgs& m,
+                                               const i64* pz, unsigned pos, int N) {
+  const u64* bk = b + 2 * (long)m.K * nP;
+  u64 x = tb::shoup((u64)(cv + (i64)P.q), bk[0], bk[1], P.q);
+  for (int k = 0; k < m.K; ++k) {
+    const u64* bb = b + 2 * (long)k * nP;
+    x += tb::shoup((u64)(pz[(long)k * N + pos] + (i64)P.off), bb[0], bb[1], P.q);
+    x = (x >= P.q2) ? x - P.q2 : x;
+  }
+  return (i64)(x >= P.q ? x - P.q : x);
+}
+
 // inverse pass A' + exit: y = CS1(x * N^-1 R^-1)  == intt_radix2_exit_reduce of the reference (canonical).
-template <int LA, bool BIG>
+template <int LA, bool BIG, bool MD = false>
 __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, TbView dst, int prime0, int LWr,
-                                                       int mac_chain) {
+                                                       int mac_chain, TbMdArgs md) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int LB = BIG ? 8 : c.LB, LW = BIG ? 12 - LA : LWr;
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
   const int limb = blockIdx.y, g = prime0 + limb;
   const TbFastPrime P = c.fp[g];
-  const i64* s = src.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
-  i64* d = dst.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  const unsigned c0 = blockIdx.x * W + col;
+  const i64* s = src.row(blockIdx.z, limb) + c0;
+  i64* d = dst.row(blockIdx.z, limb) + c0;
+  // MD: z = ciphertext * 2 + half; the result goes to that half's output rows, with the tail applied
+  const i64 *pz = nullptr, *av = nullptr;
+  const u64* bn = nullptr;
+  int tail = 0;
+  if constexpr (MD) {
+    const int bt = blockIdx.z >> 1, h = blockIdx.z & 1;
+    d = (h ? md.out1 : md.out0).row(bt, limb) + c0;
+    av = (h ? md.add1 : md.add0).row(bt, limb) + c0;
+    tail = (md.tail == 2 && h == 1) ? 0 : md.tail;
+    pz = md.p + (long)blockIdx.z * md.pbs + c0;
+    bn = md.bn + 2 * g;
+  }
+  const int Nn = 1 << c.logN;
+  auto finish = [&](i64 y, unsigned pos) {  // canonical residue -> stored value
+    if constexpr (MD) {
+      y = tb_moddown_exit(y, P, bn, c.P, md, pz, pos, Nn);
+      if (tail == 1) y = tb_cs1(av[pos] + y, (i64)P.q);
+      if (tail == 2) y = tb_cs1(tb_add(av[pos], y, (i64)P.q2), (i64)P.q);
+    }
+    d[pos] = y;
+  };
   constexpr int f0 = tb::fwd_field<LA>(0);
   i64 x[16];
 #pragma unroll
@@ -388,7 +433,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
       double r = pol.mulmod(__longlong_as_double(x[i]), exd);  // x N^-1 R^-1, |r| < 1.1 q
       r = r < 0.0 ? __dadd_rn(r, pol.q) : r;
       r = r >= pol.q ? __dadd_rn(r, -pol.q) : r;
-      d[(unsigned)tb::tile_x(tr, i, f0) << LB] = tb::FastF64Pol::to_int(r);
+      finish(tb::FastF64Pol::to_int(r), (unsigned)tb::tile_x(tr, i, f0) << LB);
     }
     return;
   }
@@ -399,7 +444,7 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const u64 y = tb::shoup((u64)x[i], P.ex, P.ex_s, P.q);
-    d[(unsigned)tb::tile_x(tr, i, f0) << LB] = (i64)(y >= P.q ? y - P.q : y);
+    finish((i64)(y >= P.q ? y - P.q : y), (unsigned)tb::tile_x(tr, i, f0) << LB);
   }
 }
 
@@ -409,8 +454,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_inv_A(TbDevFast c, TbView src, 
 // beta (L+K) (group, limb) pairs skip ModUp and both forward passes.  d2 carries the Montgomery factor;
 // FP64 limbs keep their extensions without it and canonical (extend_prologue_f64), other limbs with it.
 __global__ void __launch_bounds__(256) k_fast_own_fill(TbDev c, TbDevFast f, const TbKsLevel* lv, TbView d2, i64* ext,
-                                                       int level, int N, int rowsE) {
-  const int r = blockIdx.y, bt = blockIdx.z, g = level + r;
+                                                       int level, int N, int rowsE, int row0) {
+  const int r = row0 + blockIdx.y, bt = blockIdx.z, g = level + r;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (j >= N) return;
   const int ng = lv->ngroups;
@@ -455,10 +500,10 @@ __device__ __forceinline__ i64 tb_norm2q(i64 x, i64 q2) {
 // cP: [2][nP] = P mod q (limbs whose sums carry no Montgomery factor: FP64 limbs) and P R mod q (others).
 __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
                                                   const i64* ext, i64* acc, int level, int N, int rowsE, int nb,
-                                                  const i64* nadd0, const i64* nadd1, const i64* cP) {
+                                                  const i64* nadd0, const i64* nadd1, const i64* cP, int row0) {
   // grid.x = nb * tiles with the batch index fastest: the nb ciphertexts of a chunk read the same key
   // tile back to back, so the key is fetched from HBM once per chunk (L2 serves the rest)
-  const int t = blockIdx.y, bt = blockIdx.x % nb;
+  const int t = row0 + blockIdx.y, bt = blockIdx.x % nb;
   const TbPrime& P = c.pr[level + t];
   const int small = f.fp[level + t].small;
   const int j = ((blockIdx.x / nb) * blockDim.x + threadIdx.x) * 2;

@@ -14,7 +14,10 @@
 // ------------------------------------------------------------------ real CUDA
 #include <cuda_runtime.h>
 #define TB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define TB_LAUNCH_DYN(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define TB_KERNEL_SHARED __shared__
+#define TB_SET_MAX_DYN_SMEM(kernel, bytes) \
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 static __device__ __forceinline__ double tb_rint(double a) { return rint(a); }
 // streaming (L2-only) accesses for data that is touched once per kernel
 static __device__ __forceinline__ long tb_ldcg(const long* p) { return __ldcg(p); }
@@ -47,6 +50,7 @@ void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body);
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define TB_KERNEL_SHARED static
+#define TB_SET_MAX_DYN_SMEM(kernel, bytes) ((void)0)
 #define __syncthreads() emu_syncthreads()
 template <class T>
 static inline T __ldg(const T* p) {
@@ -112,6 +116,21 @@ static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t
   std::memset(d, v, n);
   return 0;
 }
+typedef void* cudaEvent_t;
+#define cudaStreamNonBlocking 1
+#define cudaEventDisableTiming 2
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+  *s = nullptr;
+  return 0;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
+  *e = nullptr;
+  return 0;
+}
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) {
   *d = 0;
@@ -123,5 +142,7 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 #define TB_LAUNCH(kernel, grid, block, stream, ...) \
+  emu_launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#define TB_LAUNCH_DYN(kernel, grid, block, smem, stream, ...) \
   emu_launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
 #endif
