@@ -103,6 +103,20 @@ def test_bad_arguments_raise(h):
             s.ctx.rescale(s.octx.num_ordinary - 1, a[:1], a[:1], a[:1], a[:1])  # no level left
         with pytest.raises(Tb200Error):
             s.ctx.rotate(0, 4, a, a, None, a.copy(), a.copy())  # even galois element
+        # the engine layer derives every extent from `level`: operands with other row counts are refused
+        # before the library sees their pointers
+        with pytest.raises(Tb200Error, match="limb rows"):
+            s.ctx.cc_addsub(1, False, a, a, a, a, a.copy(), a.copy())  # level 1 has 3 rows, not 4
+        with pytest.raises(Tb200Error, match="limb rows"):
+            s.ctx.cc_mult_relin(0, a, a, a[:3], a, s.evk_d, a[:3].copy(), a[:3].copy(), True)
+        with pytest.raises(Tb200Error, match="batch"):
+            b2 = np.zeros((2, 4, s.N), dtype=np.int64)
+            s.ctx.cc_addsub(0, False, b2, b2, a, a, b2.copy(), b2.copy())
+        with pytest.raises(Tb200Error, match="rows"):
+            from tiberate_fhe_b200.context import KeySwitchKeyView
+
+            short = KeySwitchKeyView([(np.zeros((2, s.N), dtype=np.int64), np.zeros((2, s.N), dtype=np.int64))], s.N)
+            s.ctx.keyswitch(0, a, short, a.copy(), a.copy())
     finally:
         s.close()
 

@@ -205,3 +205,25 @@ def test_self_contained_round_trip():
     wr = torch.zeros(N, dtype=torch.float64, device="cuda:0")
     wr[idx % N] = torch.where(idx >= N, -va.double(), va.double())
     assert (dr - wr * scale * scale / q0).abs().max() < 1.0e-6 * scale, "Dec(rotate(Enc(a)))"
+
+
+def test_two_engines_with_different_prime_chains_share_a_gpu():
+    """key generation / encryption / decryption must use the engine's own context, not the
+    device-current one.  Engine B (another prime chain, same N) is created after engine A; A must still
+    encrypt and decrypt correctly, and so must B."""
+    import torch
+
+    import tiberate_fhe_b200 as tb
+    from oracle.context import toy_primes
+
+    a = tb.CkksEngine(14, devices=["cuda:0"], seed=list(range(8)), nonce=[1, 2])
+    b = tb.CkksEngine(dict(logN=14, q=toy_primes(14, 5, 2), num_special_primes=2), devices=["cuda:0"],
+                      seed=list(range(8, 16)), nonce=[3, 4])
+    assert a.ctx.q != b.ctx.q and a.N == b.N
+    gen = torch.Generator().manual_seed(9)
+    m = torch.randn(a.num_slots, generator=gen, dtype=torch.float64)
+    for eng in (a, b, a):
+        ct = eng.encodecrypt(m)
+        sq = eng.cc_mult(ct, ct)
+        dec = torch.as_tensor(eng.decryptcode(sq, is_real=True), dtype=torch.float64)[: m.numel()]
+        assert (dec - m * m).abs().max().item() < 1e-4, "engine mixed its parameter set with another engine's"

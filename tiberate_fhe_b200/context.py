@@ -95,6 +95,10 @@ class KeySwitchKeyView:
             k.a[g] = _ptr(a)
         k.row_stride = rs if rs is not None else N
         self.c = k
+        self.rows = next((part[0].shape[0] for part in parts if part is not None), 0)
+        for part in parts:
+            if part is not None and (part[0].shape[0] != self.rows or part[1].shape[0] != self.rows):
+                raise Tb200Error("all key-switch key parts must have the same number of rows")
 
 
 class Tb200Context:
@@ -263,12 +267,55 @@ class Tb200Context:
     def _pp(self, x):
         return C.byref(poly(x, self.N)) if x is not None else None
 
+    def _rows(self, level: int) -> int:
+        """limb rows of a polynomial at `level` in this context (local rows when limb-sharded)"""
+        if self.world == 1:
+            return self.num_ordinary - level
+        return len(self.local_rows(level))
+
+    def _shapes(self, what: str, level: int, *specs, key: KeySwitchKeyView | None = None):
+        """The C entry points take raw pointers and derive every extent from `level`: check here that each
+        operand really has that many limb rows, and that all of them agree on batch size and device.
+        specs: (name, tensor or None, expected rows, may_broadcast_batch)."""
+        if not 0 <= level < self.P_global - self.K:
+            raise Tb200Error(f"{what}: level {level} outside [0, {self.P_global - self.K})")
+        batch = dev = None
+        for name, x, rows, *opt in specs:
+            if x is None:
+                continue
+            nd = len(x.shape)
+            if nd not in (2, 3):
+                raise Tb200Error(f"{what}: {name} must be [limbs, N] or [batch, limbs, N], got shape {tuple(x.shape)}")
+            if x.shape[-2] != rows:
+                raise Tb200Error(f"{what}: {name} has {x.shape[-2]} limb rows, level {level} needs {rows} "
+                                 f"(shape {tuple(x.shape)}; ciphertexts that include the special limbs are not "
+                                 f"accepted here)")
+            b = x.shape[0] if nd == 3 else 1
+            if not (opt and opt[0] and nd == 2):
+                if batch is None:
+                    batch = b
+                elif b != batch:
+                    raise Tb200Error(f"{what}: {name} has batch {b}, the other operands {batch}")
+            d = None if isinstance(x, np.ndarray) else x.device
+            if d is not None and not (d.type == "cpu" and "emu" in getattr(self.lib, "path", "")):  # tests/emu: host tensors
+                if d.type != "cuda" or (d.index if d.index is not None else 0) != self.device:
+                    raise Tb200Error(f"{what}: {name} lives on {d}, the context on cuda:{self.device}")
+                dev = d
+        if key is not None and key.rows != len(self.local_prime_ids):
+            raise Tb200Error(f"{what}: key-switch key parts have {key.rows} rows, the context has "
+                             f"{len(self.local_prime_ids)} primes")
+        _ = dev
+
     def rescale(self, level: int, in0, in1, out0, out1, exact: bool = True):
+        r = self._rows(level)
+        self._shapes("rescale", level, ("in0", in0, r), ("in1", in1, r), ("out0", out0, r - 1), ("out1", out1, r - 1))
         rc = self.lib.tb200_rescale(self.h, level, self._batch(in0), self._pp(in0), self._pp(in1), self._pp(out0),
                                     self._pp(out1), int(exact), _stream(out0))
         self.lib.check(rc, "rescale")
 
     def keyswitch(self, level: int, a, ksk: KeySwitchKeyView, out0, out1):
+        r = self._rows(level)
+        self._shapes("keyswitch", level, ("a", a, r), ("out0", out0, r), ("out1", out1, r), key=ksk)
         rc = self.lib.tb200_keyswitch(self.h, level, self._batch(a), self._pp(a), C.byref(ksk.c), self._pp(out0),
                                       self._pp(out1), _stream(out0))
         self.lib.check(rc, "keyswitch")
@@ -290,40 +337,62 @@ class Tb200Context:
         self.lib.check(rc, "ks_digits")
 
     def ks_finish(self, level: int, state, ksk: KeySwitchKeyView, out0, out1, add0=None, add1=None, tail: int = 0):
+        r = self._rows(level)
+        self._shapes("ks_finish", level, ("state", state, self.ks_state_info(level)[0]), ("out0", out0, r),
+                     ("out1", out1, r), ("add0", add0, r), ("add1", add1, r), key=ksk)
         rc = self.lib.tb200_ks_finish(self.h, level, self._batch(state), self._pp(state), C.byref(ksk.c),
                                       self._pp(add0), self._pp(add1), self._pp(out0), self._pp(out1), int(tail),
                                       _stream(out0))
         self.lib.check(rc, "ks_finish")
 
     def cc_mult_relin(self, level: int, a0, a1, b0, b1, evk: KeySwitchKeyView, out0, out1, pre_rescale: bool = True):
+        r = self._rows(level)
+        ro = r - (1 if pre_rescale else 0)
+        self._shapes("cc_mult_relin", level, ("a0", a0, r), ("a1", a1, r), ("b0", b0, r), ("b1", b1, r),
+                     ("out0", out0, ro), ("out1", out1, ro), key=evk)
         rc = self.lib.tb200_cc_mult_relin(self.h, level, self._batch(a0), self._pp(a0), self._pp(a1), self._pp(b0),
                                           self._pp(b1), C.byref(evk.c), self._pp(out0), self._pp(out1),
                                           int(pre_rescale), _stream(out0))
         self.lib.check(rc, "cc_mult_relin")
 
     def cc_mult_triplet(self, level: int, a0, a1, b0, b1, d0, d1, d2, pre_rescale: bool = True):
+        r = self._rows(level)
+        ro = r - (1 if pre_rescale else 0)
+        self._shapes("cc_mult_triplet", level, ("a0", a0, r), ("a1", a1, r), ("b0", b0, r), ("b1", b1, r),
+                     ("d0", d0, ro), ("d1", d1, ro), ("d2", d2, ro))
         rc = self.lib.tb200_cc_mult_triplet(self.h, level, self._batch(a0), self._pp(a0), self._pp(a1), self._pp(b0),
                                             self._pp(b1), self._pp(d0), self._pp(d1), self._pp(d2), int(pre_rescale),
                                             _stream(d0))
         self.lib.check(rc, "cc_mult_triplet")
 
     def relinearize(self, level: int, d0, d1, d2, evk: KeySwitchKeyView, out0, out1):
+        r = self._rows(level)
+        self._shapes("relinearize", level, ("d0", d0, r), ("d1", d1, r), ("d2", d2, r), ("out0", out0, r),
+                     ("out1", out1, r), key=evk)
         rc = self.lib.tb200_relinearize(self.h, level, self._batch(d0), self._pp(d0), self._pp(d1), self._pp(d2),
                                         C.byref(evk.c), self._pp(out0), self._pp(out1), _stream(out0))
         self.lib.check(rc, "relinearize")
 
     def rotate(self, level: int, galois: int, c0, c1, rotk: KeySwitchKeyView | None, out0, out1):
+        r = self._rows(level)
+        self._shapes("rotate", level, ("c0", c0, r), ("c1", c1, r), ("out0", out0, r), ("out1", out1, r), key=rotk)
         rc = self.lib.tb200_rotate(self.h, level, self._batch(c0), int(galois), self._pp(c0), self._pp(c1),
                                    C.byref(rotk.c) if rotk is not None else None, self._pp(out0), self._pp(out1),
                                    _stream(out0))
         self.lib.check(rc, "rotate")
 
     def switch_key(self, level: int, c0, c1, ksk: KeySwitchKeyView, out0, out1):
+        r = self._rows(level)
+        self._shapes("switch_key", level, ("c0", c0, r), ("c1", c1, r), ("out0", out0, r), ("out1", out1, r), key=ksk)
         rc = self.lib.tb200_switch_key(self.h, level, self._batch(c0), self._pp(c0), self._pp(c1), C.byref(ksk.c),
                                        self._pp(out0), self._pp(out1), _stream(out0))
         self.lib.check(rc, "switch_key")
 
     def pc_mult(self, level: int, pt, c0, c1, out0, out1, post_rescale: bool = True):
+        r = self._rows(level)
+        ro = r - (1 if post_rescale else 0)
+        self._shapes("pc_mult", level, ("pt", pt, r, True), ("c0", c0, r), ("c1", c1, r), ("out0", out0, ro),
+                     ("out1", out1, ro))
         ppt = poly(pt, self.N)
         if len(pt.shape) == 2:
             ppt.batch_stride = 0
@@ -332,6 +401,9 @@ class Tb200Context:
         self.lib.check(rc, "pc_mult")
 
     def cc_addsub(self, level: int, sub: bool, a0, a1, b0, b1, out0, out1):
+        r = self._rows(level)
+        self._shapes("cc_addsub", level, ("a0", a0, r), ("a1", a1, r), ("b0", b0, r), ("b1", b1, r),
+                     ("out0", out0, r), ("out1", out1, r))
         rc = self.lib.tb200_cc_addsub(self.h, level, self._batch(a0), int(sub), self._pp(a0), self._pp(a1),
                                       self._pp(b0), self._pp(b1), self._pp(out0), self._pp(out1), _stream(out0))
         self.lib.check(rc, "cc_addsub")

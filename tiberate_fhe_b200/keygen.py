@@ -18,7 +18,7 @@ import torch
 
 from .context import galois_element
 from .typing import FLAGS, Ciphertext, EvaluationKey, KeySwitchKey, PublicKey, RotationKey, SecretKey
-from .wrapper import mont_ops, ntt2_ops
+from . import wrapper
 
 
 class _RotationKeys(dict):
@@ -51,19 +51,23 @@ class KeyGenMixin:
         return self._consts[key]
 
     def _tile_unsigned(self, a, lvl=0, mult_type=-1):
-        return mont_ops.tile_unsigned(a, [self._two_q(lvl, mult_type)])
+        return self.mont_ops.tile_unsigned(a, [self._two_q(lvl, mult_type)])
 
     def _enter_ntt(self, a, mult_type=-1):
-        ntt2_ops.enter_ntt_radix2(a, None, None, None, self._sp(mult_type))
+        self.ntt2_ops.enter_ntt_radix2(a, None, None, None, self._sp(mult_type))
 
     def _intt_exit(self, a, mult_type=-1):
-        ntt2_ops.intt_radix2_exit(a, None, None, None, self._sp(mult_type))
+        self.ntt2_ops.intt_radix2_exit(a, None, None, None, self._sp(mult_type))
 
     # ---- constants (ckks_engine.py:241-291) --------------------------------------------------------
     def _init_keygen(self, seed=None, nonce=None):
         from .rng import Csprng
 
         ctx = self.ctx
+        # the op-layer wrappers bound to THIS engine's context (not the device-current one)
+        self.mont_ops = wrapper.bind(wrapper.mont_ops, ctx)
+        self.ntt2_ops = wrapper.bind(wrapper.ntt2_ops, ctx)
+        self.he_ops = wrapper.bind(wrapper.he_ops, ctx)
         self._consts = {}
         self.rng = Csprng(num_coefs=self.N, num_channels=[ctx.num_ordinary],
                           num_repeating_channels=max(ctx.K, 2), devices=[str(self.device)], seed=seed, nonce=nonce)
@@ -136,8 +140,8 @@ class KeyGenMixin:
         repeats = self.ctx.K if sk.has_flag(FLAGS.INCLUDE_SPECIAL) else 0
         if a is None:
             a = self.rng.randint([[self.ctx.q[i] for i in self._primes(0, mult_type)]], repeats=repeats)
-        sa = mont_ops.mont_mult(a, sk.data, self._sp(mult_type))
-        pk0 = mont_ops.mont_sub(e, sa, self._sp(mult_type))
+        sa = self.mont_ops.mont_mult(a, sk.data, self._sp(mult_type))
+        pk0 = self.mont_ops.mont_sub(e, sa, self._sp(mult_type))
         return PublicKey(data=[pk0, a], flags=(FLAGS.INCLUDE_SPECIAL if include_special else FLAGS(0))
                          | FLAGS.MONTGOMERY_STATE | FLAGS.NTT_STATE, level=0, logN=self.logN)
 
@@ -152,19 +156,19 @@ class KeyGenMixin:
         e0_t = self._tile_unsigned(e0, level, mult_type)
         e1_t = self._tile_unsigned(e1, level, mult_type)
         pt_t = self._tile_unsigned(pt, level, mult_type)
-        mont_ops.mont_enter_Rs_scale(pt_t, sp)
-        mont_ops.mont_reduce(pt_t, sp)
-        pte0 = mont_ops.mont_add(pt_t, e0_t, sp)
+        self.mont_ops.mont_enter_Rs_scale(pt_t, sp)
+        self.mont_ops.mont_reduce(pt_t, sp)
+        pte0 = self.mont_ops.mont_add(pt_t, e0_t, sp)
         pk0, pk1 = [pk.data[0][0][level:]], [pk.data[1][0][level:]]
         v = self.rng.randint(amax=2, shift=0, repeats=1)
         v = self._tile_unsigned(v, level, mult_type)
         self._enter_ntt(v, mult_type)
-        vpk0 = mont_ops.mont_mult(v, pk0, sp)
-        vpk1 = mont_ops.mont_mult(v, pk1, sp)
+        vpk0 = self.mont_ops.mont_mult(v, pk0, sp)
+        vpk1 = self.mont_ops.mont_mult(v, pk1, sp)
         self._intt_exit(vpk0, mult_type)
         self._intt_exit(vpk1, mult_type)
-        ct0 = mont_ops.mont_add_reduce_2q(vpk0, pte0, sp)
-        ct1 = mont_ops.mont_add_reduce_2q(vpk1, e1_t, sp)
+        ct0 = self.mont_ops.mont_add_reduce_2q(vpk0, pte0, sp)
+        ct1 = self.mont_ops.mont_add_reduce_2q(vpk1, e1_t, sp)
         # (the reference's `encrypt` tags its output NTT|MONTGOMERY although it is in neither state,
         # ckks_engine.py:621-629; `encodecrypt` :2259-2267 tags it correctly -- followed here)
         return Ciphertext(data=[ct0, ct1], flags=(FLAGS.INCLUDE_SPECIAL if pk.has_flag(FLAGS.INCLUDE_SPECIAL)
@@ -175,10 +179,10 @@ class KeyGenMixin:
         base_at = -self.ctx.K - 1 if include_special else -1
         base = pt[0][base_at][None, :]
         scaler = pt[0][0][None, :]
-        scaled = mont_ops.mont_sub([base], [scaler], self.ctx.K)
-        mont_ops.mont_enter_scalar(scaled, [self.final_scalar[level]], self.ctx.K)
-        mont_ops.reduce_2q(scaled, self.ctx.K)
-        mont_ops.make_signed(scaled, self.ctx.K)
+        scaled = self.mont_ops.mont_sub([base], [scaler], self.ctx.K)
+        self.mont_ops.mont_enter_scalar(scaled, [self.final_scalar[level]], self.ctx.K)
+        self.mont_ops.reduce_2q(scaled, self.ctx.K)
+        self.mont_ops.make_signed(scaled, self.ctx.K)
         if final_round:
             # the reference reads qlists[0][-K-2]: the LAST scale prime at every level (ckks_engine.py:696-703)
             rounding_prime = self.ctx.q[self.ctx.num_ordinary - 2]
@@ -193,9 +197,9 @@ class KeyGenMixin:
         sk_data = sk.data[0][level:]
         a = ct.data[1][0].clone()
         self._enter_ntt([a])
-        sa = mont_ops.mont_mult([a], [sk_data], self.ctx.K)
+        sa = self.mont_ops.mont_mult([a], [sk_data], self.ctx.K)
         self._intt_exit(sa)
-        pt = mont_ops.mont_add_reduce_2q([ct0], sa, self.ctx.K)
+        pt = self.mont_ops.mont_add_reduce_2q([ct0], sa, self.ctx.K)
         return self._final_scale(pt, level, ct.has_flag(FLAGS.INCLUDE_SPECIAL), final_round)
 
     def decrypt_triplet(self, ct_mult, sk: SecretKey = None, *, final_round=True):
@@ -203,15 +207,15 @@ class KeyGenMixin:
         level, K = ct_mult.level, self.ctx.K
         d0 = [ct_mult.data[0][0].clone()]
         d1, d2 = [ct_mult.data[1][0]], [ct_mult.data[2][0]]
-        ntt2_ops.intt_radix2_exit_reduce(d0, None, None, None, K)
+        self.ntt2_ops.intt_radix2_exit_reduce(d0, None, None, None, K)
         sk_data = [sk.data[0][level:]]
-        d1_s = mont_ops.mont_mult(d1, sk_data, K)
-        s2 = mont_ops.mont_mult(sk_data, sk_data, K)
-        d2_s2 = mont_ops.mont_mult(d2, s2, K)
+        d1_s = self.mont_ops.mont_mult(d1, sk_data, K)
+        s2 = self.mont_ops.mont_mult(sk_data, sk_data, K)
+        d2_s2 = self.mont_ops.mont_mult(d2, s2, K)
         self._intt_exit(d1_s)
         self._intt_exit(d2_s2)
-        pt = mont_ops.mont_add(d0, d1_s, K)
-        pt = mont_ops.mont_add_reduce_2q(pt, d2_s2, K)
+        pt = self.mont_ops.mont_add(d0, d1_s, K)
+        pt = self.mont_ops.mont_add_reduce_2q(pt, d2_s2, K)
         return self._final_scale(pt, level, ct_mult.has_flag(FLAGS.INCLUDE_SPECIAL), final_round)
 
     def decrypt(self, ct, sk: SecretKey = None, *, final_round=True):
@@ -234,7 +238,7 @@ class KeyGenMixin:
             if not (k.has_flag(FLAGS.NTT_STATE) and k.has_flag(FLAGS.MONTGOMERY_STATE)):
                 raise ValueError("key-switching keys are built from NTT + Montgomery secret keys")
         Psk = [sk_from.data[0][: self.ctx.num_ordinary].clone()]
-        mont_ops.mont_enter_scalar(Psk, self.mont_PR, self.ctx.K)
+        self.mont_ops.mont_enter_scalar(Psk, self.mont_PR, self.ctx.K)
         two_q = self._two_q(0, -2)
         ksk = []
         for gid, part in enumerate(self._groups()):
@@ -242,7 +246,7 @@ class KeyGenMixin:
             pk = self._create_public_key(sk_to, include_special=True, a=crs)
             lo, hi = part[0], part[-1] + 1
             pk_rows = pk.data[0][0][lo:hi]
-            upd = mont_ops.mont_add_legacy([pk_rows], [Psk[0][lo:hi]], [two_q[lo:hi]])[0]
+            upd = self.mont_ops.mont_add_legacy([pk_rows], [Psk[0][lo:hi]], [two_q[lo:hi]])[0]
             pk_rows.copy_(upd)
             pk.misc["description"] = f"key switch key part index {gid}"
             ksk.append(pk)
@@ -251,7 +255,7 @@ class KeyGenMixin:
 
     def _create_evk(self, sk: SecretKey = None) -> EvaluationKey:
         sk = sk or self.sk
-        sk2 = EvaluationKey(data=mont_ops.mont_mult(sk.data, sk.data, 0),
+        sk2 = EvaluationKey(data=self.mont_ops.mont_mult(sk.data, sk.data, 0),
                             flags=FLAGS.MONTGOMERY_STATE | FLAGS.NTT_STATE | FLAGS.INCLUDE_SPECIAL, level=sk.level)
         return EvaluationKey.wrap(self.create_key_switching_key(sk2, sk))
 
@@ -267,9 +271,9 @@ class KeyGenMixin:
     def _create_rotation_key(self, delta: int, a=None, sk: SecretKey = None) -> RotationKey:
         sk = sk or self.sk
         s = [x.clone() for x in sk.data]
-        ntt2_ops.intt_radix2(s, None, None, None, self.ctx.K)  # NTTContext defaults: mult_type -1
+        self.ntt2_ops.intt_radix2(s, None, None, None, self.ctx.K)  # NTTContext defaults: mult_type -1
         s = [self._rotate_coefficients(x, delta) for x in s]
-        ntt2_ops.ntt_radix2(s, None, None, None, self.ctx.K)
+        self.ntt2_ops.ntt_radix2(s, None, None, None, self.ctx.K)
         sk_rot = SecretKey(data=s, flags=FLAGS.MONTGOMERY_STATE | FLAGS.NTT_STATE, level=0, logN=self.logN)
         return RotationKey.wrap(self.create_key_switching_key(sk_rot, sk, a=a), delta=delta)
 
@@ -338,19 +342,19 @@ class CodecMixin:
         pt_t = self._tile_unsigned(encoded, level, mult_type)
         if dc_rns is not None:
             pt_t[0][:, 0] += dc_rns
-        mont_ops.mont_enter_Rs_scale(pt_t, sp)
-        mont_ops.mont_reduce(pt_t, sp)
-        pte0 = mont_ops.mont_add(pt_t, e0_t, sp)
+        self.mont_ops.mont_enter_Rs_scale(pt_t, sp)
+        self.mont_ops.mont_reduce(pt_t, sp)
+        pte0 = self.mont_ops.mont_add(pt_t, e0_t, sp)
         pk0, pk1 = [pk.data[0][0][level:]], [pk.data[1][0][level:]]
         v = self.rng.randint(amax=2, shift=0, repeats=1)
         v = self._tile_unsigned(v, level, mult_type)
         self._enter_ntt(v, mult_type)
-        vpk0 = mont_ops.mont_mult(v, pk0, sp)
-        vpk1 = mont_ops.mont_mult(v, pk1, sp)
+        vpk0 = self.mont_ops.mont_mult(v, pk0, sp)
+        vpk1 = self.mont_ops.mont_mult(v, pk1, sp)
         self._intt_exit(vpk0, mult_type)
         self._intt_exit(vpk1, mult_type)
-        ct0 = mont_ops.mont_add_reduce_2q(vpk0, pte0, sp)
-        ct1 = mont_ops.mont_add_reduce_2q(vpk1, e1_t, sp)
+        ct0 = self.mont_ops.mont_add_reduce_2q(vpk0, pte0, sp)
+        ct1 = self.mont_ops.mont_add_reduce_2q(vpk1, e1_t, sp)
         return Ciphertext(data=[ct0, ct1], flags=(FLAGS.INCLUDE_SPECIAL if pk.has_flag(FLAGS.INCLUDE_SPECIAL)
                                                    else FLAGS(0)), level=level, logN=self.logN)
 
@@ -363,23 +367,23 @@ class CodecMixin:
         sk_data = sk.data[0][level:]
         if isinstance(ct, CiphertextTriplet):
             d0 = [ct.data[0][0].clone()]
-            ntt2_ops.intt_radix2_exit_reduce(d0, None, None, None, K)
-            d1_s = mont_ops.mont_mult([ct.data[1][0]], [sk_data], K)
-            s2 = mont_ops.mont_mult([sk_data], [sk_data], K)
-            d2_s2 = mont_ops.mont_mult([ct.data[2][0]], s2, K)
+            self.ntt2_ops.intt_radix2_exit_reduce(d0, None, None, None, K)
+            d1_s = self.mont_ops.mont_mult([ct.data[1][0]], [sk_data], K)
+            s2 = self.mont_ops.mont_mult([sk_data], [sk_data], K)
+            d2_s2 = self.mont_ops.mont_mult([ct.data[2][0]], s2, K)
             self._intt_exit(d1_s)
             self._intt_exit(d2_s2)
-            pt = mont_ops.mont_add(d0, d1_s, K)
-            pt = mont_ops.mont_add(pt, d2_s2, K)
-            mont_ops.reduce_2q(pt, K)
+            pt = self.mont_ops.mont_add(d0, d1_s, K)
+            pt = self.mont_ops.mont_add(pt, d2_s2, K)
+            self.mont_ops.reduce_2q(pt, K)
         else:
             self._require_plain(ct)
             a = ct.data[1][0].clone()
             self._enter_ntt([a])
-            sa = mont_ops.mont_mult([a], [sk_data], K)
+            sa = self.mont_ops.mont_mult([a], [sk_data], K)
             self._intt_exit(sa)
-            pt = mont_ops.mont_add([ct.data[0][0]], sa, K)
-            mont_ops.reduce_2q(pt, K)
+            pt = self.mont_ops.mont_add([ct.data[0][0]], sa, K)
+            self.mont_ops.reduce_2q(pt, K)
         include_special = ct.has_flag(FLAGS.INCLUDE_SPECIAL)
         base_at = -K - 1 if include_special else -1
         base = pt[0][base_at][None, :]
@@ -398,10 +402,10 @@ class CodecMixin:
             dc = (dc0 * pow(Q0, -1, q0) * Q0 + dc1 * pow(Q1, -1, q1) * Q1 + dc2 * pow(Q2, -1, q2) * Q2) % Q
             dc = dc if dc <= Q // 2 else dc - Q
             dc = (dc + (q1 - 1)) // q1
-        scaled = mont_ops.mont_sub([base], [scaler], K)
-        mont_ops.mont_enter_scalar(scaled, [self.final_scalar[level]], K)
-        mont_ops.reduce_2q(scaled, K)
-        mont_ops.make_signed(scaled, K)
+        scaled = self.mont_ops.mont_sub([base], [scaler], K)
+        self.mont_ops.mont_enter_scalar(scaled, [self.final_scalar[level]], K)
+        self.mont_ops.reduce_2q(scaled, K)
+        self.mont_ops.make_signed(scaled, K)
         if final_round:
             rounding_prime = self.ctx.q[self.ctx.num_ordinary - 2]
             scaled[0] += (scaler[0] > (rounding_prime // 2)) * 1
@@ -423,17 +427,16 @@ class CodecMixin:
             p = self.encode(m, level, scale=pt.scale)
             p = self._tile_unsigned(p, level)
             if kind == "pc_add":
-                mont_ops.mont_enter_Rs_scale(p, self.ctx.K)
+                self.mont_ops.mont_enter_Rs_scale(p, self.ctx.K)
             else:
                 self._enter_ntt(p)
             cache[kind] = p
         return cache[kind]
 
     def pc_add(self, pt, ct: Ciphertext, inplace: bool = False) -> Ciphertext:
-        from .wrapper import he_ops
 
         p = self._plain_operand(pt, ct.level, "pc_add")
-        new_d0 = he_ops.pc_add_fused(ct.data[0], p, self.ctx.K)
+        new_d0 = self.he_ops.pc_add_fused(ct.data[0], p, self.ctx.K)
         if inplace:
             ct.data[0] = new_d0
             return ct
@@ -502,10 +505,10 @@ class LevelMixin:
         mult = [torch.tensor([(deviated_delta * (1 << 62)) % self.ctx.q[i] for i in self._primes(dst_level, -1)],
                              dtype=torch.int64, device=self.device)]
         K = self.ctx.K
-        mont_ops.mont_enter_scalar(d0, mult, K)
-        mont_ops.mont_enter_scalar(d1, mult, K)
-        mont_ops.reduce_2q(d0, K)
-        mont_ops.reduce_2q(d1, K)
+        self.mont_ops.mont_enter_scalar(d0, mult, K)
+        self.mont_ops.mont_enter_scalar(d1, mult, K)
+        self.mont_ops.reduce_2q(d0, K)
+        self.mont_ops.reduce_2q(d1, K)
         return Ciphertext(data=[d0, d1], level=dst_level, logN=self.logN, misc=dict(new_ct.misc))
 
     def negate(self, ct: Ciphertext, inplace: bool = False) -> Ciphertext:
@@ -514,5 +517,5 @@ class LevelMixin:
         for part in ct.data:
             for d in part:
                 d *= -1
-            mont_ops.make_signed(part, self.ctx.K)
+            self.mont_ops.make_signed(part, self.ctx.K)
         return ct
