@@ -81,8 +81,28 @@ def main():
     res["csprng_gaussian2_ms"] = timed(lambda: engine.rng.discrete_gaussian(repeats=2))
     res["encodecrypt_ms"] = timed(lambda: engine.encodecrypt(data))
     res["decryptcode_ms"] = timed(lambda: engine.decryptcode(ct1))
+    # The same engine object on libtb200: operators only (the reference's Python still issues every op), then with
+    # the hot methods bound to the fused entry points (tiberate_fhe_b200/backend.py) -- the drop-in numbers.
+    dropin = {}
+    try:
+        from tiberate_fhe_b200 import backend
+
+        for mode, fused in (("op_level", False), ("fused", True)):
+            with contextlib.redirect_stdout(io.StringIO()):
+                backend.install_as_tiberate_backend(engine, fused=fused)
+            try:
+                d = {"cc_mult_relin_ms": timed(lambda: engine.cc_mult(ct1, ct2, evk)),
+                     "rotate_single_ms": timed(lambda: engine.rotate_single(ct1, rotk)),
+                     "rescale_ms": timed(lambda: engine.rescale(ct1))}
+                d["hmult_relin_ops_per_s"] = 1e3 / d["cc_mult_relin_ms"]
+                d["speedup_vs_reference_ext"] = res["cc_mult_relin_ms"] / d["cc_mult_relin_ms"]
+                dropin[mode] = d
+            finally:
+                backend.uninstall()
+    except Exception as e:  # the baseline figures above stay valid
+        dropin["error"] = repr(e)
     out = {
-        "impl": "reference_cuda_ext", "logN": args.logN, "N": N, "limbs_level0": L,
+        "impl": "reference_cuda_ext", "logN": args.logN, "N": N, "limbs_level0": L, "dropin": dropin,
         "iters": args.iters, "warmup": args.warmup,
         "hmult_relin_ops_per_s": 1e3 / res["cc_mult_relin_ms"],
         "rotate_ops_per_s": 1e3 / res["rotate_single_ms"],

@@ -405,6 +405,8 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
         G.src_prime0 = li;
         G.src_row0 = li - c->lstart[l];
         lv.own[lv.nown++] = lv.ngroups;
+      } else {
+        lv.foreign[lv.nforeign++] = lv.ngroups;
       }
       lv.ngroups++;
       G.lenter_off = (long)lenter.size();

@@ -433,6 +433,8 @@ struct TbKsLevel {
   int seg_rows;          // rows of one rank's segment
   int pad;
   int own[TB_MAXG];      // indices into g[] of the owned groups
+  int nforeign;          // groups whose digits arrive from other ranks (limb sharding), indices in foreign[]
+  int foreign[TB_MAXG];
   TbKsGroup g[TB_MAXG];
 };
 

@@ -46,6 +46,8 @@ struct TbFwdAArgs {
   const double* lenterd;  // EXTEND, FP64 limbs: L_{k-1} mod q centred (no Montgomery factor), same indexing
   int prime0, LW, ngroups;
   int skip_own;           // EXTEND: the (group, own limb) pairs were pre-filled by k_fast_own_fill
+  int sel;                // EXTEND: 0 = every group, 1 = the groups this rank owns, 2 = the other ranks' groups
+  int nsel;               // EXTEND: number of selected groups (grid.z = batch * nsel)
 };
 
 template <int PRO>
@@ -193,12 +195,16 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64A_MINB : (PRO == TB_FPRO_
   const int limb = blockIdx.y, g = a.prime0 + limb;
   const TbFastPrime P = c.fp[g];
   int bt = blockIdx.z, gi = 0;
+  int dz = blockIdx.z;  // batch index of the destination rows
   if constexpr (PRO == TB_FPRO_EXTEND) {
-    gi = blockIdx.z % a.ngroups;
-    bt = blockIdx.z / a.ngroups;
+    gi = blockIdx.z % a.nsel;
+    bt = blockIdx.z / a.nsel;
+    if (a.sel == 1) gi = a.lv->own[gi];
+    if (a.sel == 2) gi = a.lv->foreign[gi];
+    dz = bt * a.ngroups + gi;
   }
   const unsigned c0 = blockIdx.x * W + col;
-  i64* d = a.dst.row(blockIdx.z, limb) + c0;
+  i64* d = a.dst.row(dz, limb) + c0;
   constexpr int f0 = tb::fwd_field<LA>(0);
   i64 x[16];
   if constexpr (PRO == TB_FPRO_EXTEND) {
