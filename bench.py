@@ -421,6 +421,17 @@ def run_ours(args):
         cpu = {"value": 1.0 / min(times), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "best of 2 x 1 HMult+relin of one logN16 ciphertext pair (oracle port, NumPy + C/OpenMP)"}
 
+    # ---- BASELINE configs[3] beside the batch-sharded figure: the limb-sharded logN17 key switch over the same
+    # ranks (strong scaling, one NCCL all-gather per key switch; asserts bit-equality with the unsharded call)
+    limb = None
+    if world > 1 and not args.quick:
+        del a0, a1, b0, b1, out0, out1, hin, hout, din, dout
+        ctx.close()
+        torch.cuda.empty_cache()
+        import bench_limb
+
+        limb = bench_limb.run(rank, world, local, steps=max(3, args.steps), warmup=3)
+
     if rank == 0:
         alg_bytes = (6 * L + 4 + 2 * ng * E) * N * 8  # SURVEY.md 8(d), un-amortised
         line = {
@@ -435,7 +446,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "reference_cuda_ext": ref_ext, "kernel_time_share": shares, "kernel_us_per_op": kernel_us_per_op,
             "hmult_hbm_roofline": {"algorithmic_bytes_per_op": alg_bytes, "roofline_ops_per_s": peak * 1e9 / alg_bytes,
                                    "frac": value / world / (peak * 1e9 / alg_bytes)},
-            "extra": extra,
+            "extra": extra, "limb_sharded": limb,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -456,11 +467,18 @@ def main():
                     help="eighths of the 40-bit-prime limbs transformed on the FP64 pipe (default: library default)")
     ap.add_argument("--tune", action="append", help="knob=value of tb200_ctx_set_tuning (A/B measurements)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="batch", choices=["batch", "limb"],
+                    help="batch: BASELINE configs[2] (the contract line); limb: configs[3], limb-sharded logN17 key switch")
     ap.add_argument("--quick", action="store_true", help="skip the secondary rotate / NTT figures and the reference ext")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "limb":
+        import bench_limb
+
+        sys.argv = [sys.argv[0], "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        bench_limb.main()
     else:
         run_ours(args)
 

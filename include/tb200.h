@@ -188,6 +188,14 @@ int tb200_ks_digits(tb200_ctx*, int level, int batch, const tb200_poly* a, const
 int tb200_ks_finish(tb200_ctx*, int level, int batch, const tb200_poly* state, const tb200_ksk* ksk,
                     const tb200_poly* add0, const tb200_poly* add1, const tb200_poly* out0, const tb200_poly* out1,
                     int tail, tb200_stream);
+/* tb200_ks_finish in two calls, so that the ModUp of the digit groups this rank owns runs while the all-gather
+ * of the other ranks' digits is still in flight (tiberate_fhe_b200/dist.py): tb200_ks_modup(which = 1 own /
+ * 2 foreign / 0 all) extends + forward-transforms (pass A) the selected groups into the context workspace,
+ * tb200_ks_core does the rest.  batch <= chunk (the extended limbs live in the workspace between the calls). */
+int tb200_ks_modup(tb200_ctx*, int level, int batch, const tb200_poly* state, int which, tb200_stream);
+int tb200_ks_core(tb200_ctx*, int level, int batch, const tb200_poly* state, const tb200_ksk* ksk,
+                  const tb200_poly* add0, const tb200_poly* add1, const tb200_poly* out0, const tb200_poly* out1,
+                  int tail, tb200_stream);
 /* cc_mult (+relinearize) :1640-1732.  a*, b*: [L_in][N] at `level`; with pre_rescale the product
  * lives at level+1 and has L_in-1 rows.  out0/out1 canonical coefficient domain. */
 int tb200_cc_mult_relin(tb200_ctx*, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,

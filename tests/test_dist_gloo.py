@@ -100,6 +100,18 @@ def _sharded_ks_worker(rank, world, port, seed):
             ks(level, a_loc, key, o0, o1)
             rows = [g - level for g in ctx.local_rows(level)]
             assert np.array_equal(o0.numpy(), want0[rows]) and np.array_equal(o1.numpy(), want1[rows]), (rank, level)
+        # batched: [B, L_local, N] through one all-gather (state stored [rows, B, N])
+        ctx.set_chunk(3)
+        for level in (0, 2):
+            lp = octx.level_primes(level, False)
+            ab = np.stack([eng.uniform(rng, lp) for _ in range(3)])
+            rows = [g - level for g in ctx.local_rows(level)]
+            a_loc = torch.from_numpy(np.ascontiguousarray(ab[:, rows]))
+            o0, o1 = torch.zeros_like(a_loc), torch.zeros_like(a_loc)
+            ks(level, a_loc, key, o0, o1)
+            for b in range(3):
+                w0, w1 = eng.create_switcher(ab[b], evk, level)
+                assert np.array_equal(o0[b].numpy(), w0[rows]) and np.array_equal(o1[b].numpy(), w1[rows]), (rank, level, b)
         # limb-sharded rescale: the owner of the dropped prime broadcasts it, every rank rescales its rows
         from tiberate_fhe_b200.dist import LimbShardedRescale
 
@@ -112,6 +124,37 @@ def _sharded_ks_worker(rank, world, port, seed):
             o0, o1 = rs(level, loc[0], loc[1])
             rows = [g - level - 1 for g in ctx.local_rows(level + 1)]
             assert np.array_equal(o0.numpy(), want[0][rows]) and np.array_equal(o1.numpy(), want[1][rows]), (rank, level)
+        # whole operations on sharded ciphertexts (dist.LimbShardedOps): rotate_single and cc_mult + relinearize,
+        # with and without the overlapped (split-call) key switch
+        from tiberate_fhe_b200.context import galois_element
+        from tiberate_fhe_b200.dist import LimbShardedOps
+
+        def local_key(k):
+            return KeySwitchKeyView([None if p is None else (torch.from_numpy(np.ascontiguousarray(p[0][ids])),
+                                                             torch.from_numpy(np.ascontiguousarray(p[1][ids]))) for p in k],
+                                    octx.N)
+
+        delta = 3
+        rotk = eng.gen_rotk(rng, sk, delta)
+        rotk_loc, evk_loc = local_key(rotk), key
+        for overlap in (True, False):
+            ops = LimbShardedOps(ctx, overlap=overlap)
+            for level in (0, 1, 3):
+                lp = octx.level_primes(level, False)
+                ct1 = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+                ct2 = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+                l1 = [shard_rows(torch.from_numpy(x), ctx, level) for x in ct1]
+                l2 = [shard_rows(torch.from_numpy(x), ctx, level) for x in ct2]
+                want = eng.rotate_single(ct1, rotk, delta, level)
+                o0, o1 = ops.rotate(level, galois_element(octx.N, delta), l1[0], l1[1], rotk_loc)
+                rows = [g - level for g in ctx.local_rows(level)]
+                assert np.array_equal(o0.numpy(), want[0][rows]) and np.array_equal(o1.numpy(), want[1][rows]), \
+                    ("rotate", rank, level, overlap)
+                want, lvl1 = eng.cc_mult(ct1, ct2, evk, level, pre_rescale=True)
+                o0, o1 = ops.cc_mult_relin(level, l1[0], l1[1], l2[0], l2[1], evk_loc)
+                rows = [g - lvl1 for g in ctx.local_rows(lvl1)]
+                assert np.array_equal(o0.numpy(), want[0][rows]) and np.array_equal(o1.numpy(), want[1][rows]), \
+                    ("cc_mult_relin", rank, level, overlap)
         ctx.close()
     finally:
         dist.destroy_process_group()

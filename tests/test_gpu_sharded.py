@@ -70,6 +70,32 @@ def _worker(rank, world, port):
             rows = [g - level - 1 for g in ctx.local_rows(level + 1)]
             assert np.array_equal(r0.cpu().numpy(), want[0][rows]), (rank, level)
             assert np.array_equal(r1.cpu().numpy(), want[1][rows]), (rank, level)
+        # whole operations on sharded ciphertexts: rotate_single and cc_mult + relinearize against the oracle
+        from tiberate_fhe_b200.context import galois_element
+        from tiberate_fhe_b200.dist import LimbShardedOps
+
+        delta = 3
+        rotk = eng.gen_rotk(rng, sk, delta)
+        rotk_loc = KeySwitchKeyView([(torch.from_numpy(np.ascontiguousarray(p[0][ids])).to(dev),
+                                      torch.from_numpy(np.ascontiguousarray(p[1][ids])).to(dev)) for p in rotk], octx.N)
+        for overlap in (True, False):
+            ops = LimbShardedOps(ctx, overlap=overlap)
+            for level in (0, 2, 5):
+                lp = octx.level_primes(level, False)
+                ct1 = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+                ct2 = [eng.uniform(rng, lp), eng.uniform(rng, lp)]
+                l1 = [shard_rows(torch.from_numpy(x), ctx, level).to(dev) for x in ct1]
+                l2 = [shard_rows(torch.from_numpy(x), ctx, level).to(dev) for x in ct2]
+                want = eng.rotate_single(ct1, rotk, delta, level)
+                o0, o1 = ops.rotate(level, galois_element(octx.N, delta), l1[0], l1[1], rotk_loc)
+                rows = [g - level for g in ctx.local_rows(level)]
+                assert np.array_equal(o0.cpu().numpy(), want[0][rows]), ("rotate", rank, level, overlap)
+                assert np.array_equal(o1.cpu().numpy(), want[1][rows]), ("rotate", rank, level, overlap)
+                want, lvl1 = eng.cc_mult(ct1, ct2, evk, level, pre_rescale=True)
+                o0, o1 = ops.cc_mult_relin(level, l1[0], l1[1], l2[0], l2[1], key)
+                rows = [g - lvl1 for g in ctx.local_rows(lvl1)]
+                assert np.array_equal(o0.cpu().numpy(), want[0][rows]), ("cc_mult_relin", rank, level, overlap)
+                assert np.array_equal(o1.cpu().numpy(), want[1][rows]), ("cc_mult_relin", rank, level, overlap)
         ctx.close()
 
         # 2. logN17 (79 primes, 13 digit groups): sharded result == unsharded result of rank 0

@@ -67,6 +67,8 @@ SIGNATURES = {
     "tb200_ks_state_info": (_i, [_vp, _i, _vp]),
     "tb200_ks_digits": (_i, [_vp, _i, _i, PP, PP, _vp]),
     "tb200_ks_finish": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, PP, PP, _i, _vp]),
+    "tb200_ks_modup": (_i, [_vp, _i, _i, PP, _i, _vp]),
+    "tb200_ks_core": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_mult_relin": (_i, [_vp, _i, _i, PP, PP, PP, PP, C.POINTER(Ksk), PP, PP, _i, _vp]),
     "tb200_cc_mult_triplet": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_relinearize": (_i, [_vp, _i, _i, PP, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),

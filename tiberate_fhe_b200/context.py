@@ -345,6 +345,22 @@ class Tb200Context:
                                       _stream(out0))
         self.lib.check(rc, "ks_finish")
 
+    def ks_modup(self, level: int, state, which: int = 0):
+        """ModUp (extend + forward pass A) of the digit groups selected by `which`: 0 all, 1 the groups this
+        rank owns, 2 the others; into the context workspace (followed by ks_core)."""
+        self._shapes("ks_modup", level, ("state", state, self.ks_state_info(level)[0]))
+        rc = self.lib.tb200_ks_modup(self.h, level, self._batch(state), self._pp(state), int(which), _stream(state))
+        self.lib.check(rc, "ks_modup")
+
+    def ks_core(self, level: int, state, ksk: KeySwitchKeyView, out0, out1, add0=None, add1=None, tail: int = 0):
+        r = self._rows(level)
+        self._shapes("ks_core", level, ("state", state, self.ks_state_info(level)[0]), ("out0", out0, r),
+                     ("out1", out1, r), ("add0", add0, r), ("add1", add1, r), key=ksk)
+        rc = self.lib.tb200_ks_core(self.h, level, self._batch(state), self._pp(state), C.byref(ksk.c),
+                                    self._pp(add0), self._pp(add1), self._pp(out0), self._pp(out1), int(tail),
+                                    _stream(out0))
+        self.lib.check(rc, "ks_core")
+
     def cc_mult_relin(self, level: int, a0, a1, b0, b1, evk: KeySwitchKeyView, out0, out1, pre_rescale: bool = True):
         r = self._rows(level)
         ro = r - (1 if pre_rescale else 0)

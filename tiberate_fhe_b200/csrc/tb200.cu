@@ -1166,8 +1166,55 @@ struct TbRelinExtra {
 };
 // rows [0, nf) of a key switch at this level go through the fused core kernel
 static int ks_core_rows(const tb200_ctx* c, int p0, int E) { return (c->fast && c->fused_core) ? f64_prefix(c, p0, E) : 0; }
+// ModUp of the selected digit groups (sel: 0 every group, 1 the groups this rank owns, 2 the other ranks' groups):
+// digits -> extended limbs, with forward pass A fused in on the mod-q path.  Splitting by ownership lets a limb-
+// sharded key switch extend its own groups while the all-gather of the others is in flight (dist.py).
+static int ks_modup(tb200_ctx* c, int level, int nb, TbView state, i64* ws, tb200_stream st, bool own_prefilled, int sel) {
+  const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
+  const TbKsLevel& lv = c->ks[level];
+  const int ng = lv.ngroups;
+  const TbKsLevel* dlv = c->d_ks + level;
+  i64* ext = ws;
+  int rc = 0;
+  if (!c->fast) {  // exact op kernels: one launch over every group, issued with the last selection
+    if (sel == 1 && lv.nforeign > 0) return 0;
+    LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
+           dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), dlv, (const i64*)c->d_lenter, state, ext, p0, N, E);
+    return 0;
+  }
+  const int nsel = sel == 0 ? ng : (sel == 1 ? lv.nown : lv.nforeign);
+  if (nsel == 0) return 0;
+  TbFwdAArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.src = state;
+  fa.dst = dense(ext, E, N);
+  fa.lv = dlv;
+  fa.lenter2 = c->d_lenter2;
+  fa.lenterd = c->d_lenterd;
+  fa.prime0 = p0;
+  fa.ngroups = ng;
+  fa.skip_own = own_prefilled ? 1 : 0;
+  fa.sel = sel;
+  fa.nsel = nsel;
+  const int nf = ks_core_rows(c, p0, E);
+  const bool split_a = c->LB == 8 && ntt_lw(c) == 12 - c->LA && nf > 0;  // FP64-only pass A instantiation exists
+  if (split_a) {
+    if ((rc = launch_fast_fwd_A_rows<TB_FPRO_EXTEND, true>(c, fa, nf, nb * nsel, st))) return rc;
+    if (nf < E) {
+      TbFwdAArgs fb = fa;
+      fb.prime0 += nf;
+      fb.dst = rows_from(fb.dst, nf);
+      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_EXTEND, false>(c, fb, E - nf, nb * nsel, st))) return rc;
+    }
+    return 0;
+  }
+  return launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * nsel, st);
+}
+
+// modup_done: the caller already ran ks_modup for every group (split call of a limb-sharded key switch)
 static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskDev& key, TbView add0, TbView add1,
-                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, const TbRelinExtra* ex = nullptr) {
+                     TbView out0, TbView out1, int tail, i64* ws, tb200_stream st, const TbRelinExtra* ex = nullptr,
+                     bool modup_done = false) {
   const bool own_prefilled = ex && ex->own_prefilled;
   const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
   const TbKsLevel& lv = c->ks[level];
@@ -1177,38 +1224,16 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
   i64* acc = ext + (size_t)nb * ng * E * N;
   const TbDev d = c->dev();
   int rc = 0;
+  if (!modup_done && (rc = ks_modup(c, level, nb, state, ws, st, own_prefilled, 0))) return rc;
   if (c->fast) {
-    // ModUp extend fused into forward pass A, then pass B (mod-q path)
-    TbFwdAArgs fa;
-    memset(&fa, 0, sizeof(fa));
-    fa.src = state;
-    fa.dst = dense(ext, E, N);
-    fa.lv = dlv;
-    fa.lenter2 = c->d_lenter2;
-    fa.lenterd = c->d_lenterd;
-    fa.prime0 = p0;
-    fa.ngroups = ng;
-    fa.skip_own = own_prefilled ? 1 : 0;
     // FP64 limbs: pass B of every group + key inner product + inverse pass B' in one kernel (tb200_ks_core.cuh);
-    // the remaining limbs (60-bit base / special primes) take the three separate kernels on their rows --
-    // on a forked stream: they load the integer pipes, the FP64 rows the FP64 pipe.
+    // the remaining limbs (60-bit base / special primes) take the three separate kernels on their rows
+    // (optionally on a forked stream: they load the integer pipes, the FP64 rows the FP64 pipe).
     const int nf = ks_core_rows(c, p0, E);
-    const bool split_a = c->LB == 8 && ntt_lw(c) == 12 - c->LA && nf > 0;  // FP64-only pass A instantiation exists
     tb200_stream sst = st;
-    if (nf > 0 && nf < E && split_a && c->side_rows && !g_prof_on) {
+    if (nf > 0 && nf < E && c->side_rows && !g_prof_on) {
       if ((rc = side_stream_fork(c, st))) return rc;
       sst = (tb200_stream)c->side;
-    }
-    if (split_a) {
-      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_EXTEND, true>(c, fa, nf, nb * ng, st))) return rc;
-      if (nf < E) {
-        TbFwdAArgs fb = fa;
-        fb.prime0 += nf;
-        fb.dst = rows_from(fb.dst, nf);
-        if ((rc = launch_fast_fwd_A_rows<TB_FPRO_EXTEND, false>(c, fb, E - nf, nb * ng, sst))) return rc;
-      }
-    } else if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, E, nb * ng, st))) {
-      return rc;
     }
     if (nf > 0) {
       TbKsCoreArgs ka;
@@ -1265,8 +1290,6 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     // inverse pass A' + exit: back to coefficients, canonical
     if ((rc = launch_fast_inv_A(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, p0, 1, st))) return rc;
   } else {
-    LAUNCH(k_extend_all, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)(ng * nb)),
-           dim3(N / 2 < 256 ? N / 2 : 256), st, d, dlv, (const i64*)c->d_lenter, state, ext, p0, N, E);
     if ((rc = ntt_forward(c, dense(ext, E, N), dense(ext, E, N), E, nb * ng, p0, false, st))) return rc;
     LAUNCH(k_mac, dim3((unsigned)((N / 2 + 255) / 256), (unsigned)E, (unsigned)nb), dim3(N / 2 < 256 ? N / 2 : 256), st,
            d, dlv, key, (const i64*)ext, acc, p0, N, E);
@@ -1349,6 +1372,44 @@ extern "C" int tb200_ks_finish(tb200_ctx* c, int level, int batch, const tb200_p
   return 0;
 }
 
+// The same in two calls, for overlapping the digit all-gather of a limb-sharded key switch with the ModUp of the
+// groups this rank owns: tb200_ks_modup(which = 1) while the collective runs, tb200_ks_modup(which = 2) after it,
+// then tb200_ks_core.  The extended limbs live in the context workspace between the calls: batch <= chunk.
+extern "C" int tb200_ks_modup(tb200_ctx* c, int level, int batch, const tb200_poly* state, int which, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (which < 0 || which > 2) return fail(TB200_EINVAL, "ks_modup: which must be 0 (all), 1 (own) or 2 (foreign)");
+  if (batch > c->chunk) return fail(TB200_EINVAL, "ks_modup: batch %d exceeds the chunk %d", batch, c->chunk);
+  CHECK_POLY(state);
+  CK(cudaSetDevice(c->device));
+  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * (size_t)batch))) return rc;
+  if ((rc = ks_modup(c, level, batch, view(state), c->ws, st, false, which))) return rc;
+  POST();
+  return 0;
+}
+extern "C" int tb200_ks_core(tb200_ctx* c, int level, int batch, const tb200_poly* state, const tb200_ksk* ksk,
+                             const tb200_poly* add0, const tb200_poly* add1, const tb200_poly* out0,
+                             const tb200_poly* out1, int tail, tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (tail < 0 || tail > 2) return fail(TB200_EINVAL, "ks_core: tail must be 0, 1 or 2");
+  if (batch > c->chunk) return fail(TB200_EINVAL, "ks_core: batch %d exceeds the chunk %d", batch, c->chunk);
+  CHECK_POLY(state);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  if (tail != 0) CHECK_POLY(add0);
+  if (tail == 1) CHECK_POLY(add1);
+  TbKskDev key;
+  if ((rc = make_key(c, level, ksk, &key))) return rc;
+  CK(cudaSetDevice(c->device));
+  if (c->ws_elems < ks_ws_elems(c, level) * (size_t)batch) return fail(TB200_EINVAL, "ks_core: call tb200_ks_modup first");
+  rc = ks_finish(c, level, batch, view(state), key, view(add0 ? add0 : out0), view(add1 ? add1 : out1), view(out0),
+                 view(out1), tail, c->ws, st, nullptr, true);
+  if (rc) return rc;
+  POST();
+  return 0;
+}
+
 extern "C" int tb200_keyswitch(tb200_ctx* c, int level, int batch, const tb200_poly* a, const tb200_ksk* ksk,
                                const tb200_poly* out0, const tb200_poly* out1, tb200_stream st) {
   int rc = check_level(c, level, batch);
@@ -1402,7 +1463,7 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
                             const tb200_poly* out1, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
-  REQUIRE_UNSHARDED();
+  if (rotk) REQUIRE_UNSHARDED();  // the automorphism alone is limb-local; the key switch is dist.py's on sharded contexts
   CHECK_POLY(c0);
   CHECK_POLY(c1);
   CHECK_POLY(out0);
@@ -1411,12 +1472,12 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
     return fail(TB200_EINVAL, "galois element must be odd and in [1, 2N)");
   if (c0->ptr == out0->ptr || c1->ptr == out1->ptr) return fail(TB200_EINVAL, "rotate cannot run in place");
   CK(cudaSetDevice(c->device));
-  const int N = c->N, L = c->num_ord - level;
-  const dim3 grid = grid_pw(c, L, 1, 1);
+  const int N = c->N, L = c->num_ord - c->lstart[level];
   if (!rotk) {
-    for (int b = 0; b < batch; ++b) {
-      LAUNCH(k_automorphism, grid, dim3(256), st, c->dev(), shift(view(c0), b), shift(view(out0), b), level, (i64)galois);
-      LAUNCH(k_automorphism, grid, dim3(256), st, c->dev(), shift(view(c1), b), shift(view(out1), b), level, (i64)galois);
+    if (L > 0) {
+      const dim3 gridb((unsigned)((N + 255) / 256), (unsigned)L, (unsigned)batch);
+      LAUNCH(k_automorphism, gridb, dim3(256), st, c->dev(), view(c0), view(out0), c->lstart[level], (i64)galois);
+      LAUNCH(k_automorphism, gridb, dim3(256), st, c->dev(), view(c1), view(out1), c->lstart[level], (i64)galois);
     }
     POST();
     return 0;
@@ -1446,7 +1507,7 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
 static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbView b0, TbView b1, int pre_rescale,
                       i64* x, TbView d0, TbView d1, TbView d2, bool fast, tb200_stream st) {
   const int N = c->N;
-  const int lvl = level + (pre_rescale ? 1 : 0);
+  const int lvl = c->lstart[level + (pre_rescale ? 1 : 0)];  // index of the first alive prime in the (local) table
   const int L = c->num_ord - lvl;
   const size_t pe = (size_t)nb * L * N;
   TbView in[4] = {a0, a1, b0, b1};
@@ -1479,7 +1540,7 @@ extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const t
                                      const tb200_poly* d1, const tb200_poly* d2, int pre_rescale, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
-  REQUIRE_UNSHARDED();
+  if (pre_rescale) REQUIRE_UNSHARDED();  // the tensor product is limb-local; the rescale needs the dropped limb (dist.py)
   if (pre_rescale && level + 1 >= c->num_ord) return fail(TB200_EINVAL, "cc_mult: no level left to rescale");
   CHECK_POLY(a0);
   CHECK_POLY(a1);
@@ -1489,7 +1550,11 @@ extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const t
   CHECK_POLY(d1);
   CHECK_POLY(d2);
   CK(cudaSetDevice(c->device));
-  const int lvl = level + (pre_rescale ? 1 : 0), L = c->num_ord - lvl;
+  const int lvl = level + (pre_rescale ? 1 : 0), L = c->num_ord - c->lstart[lvl];
+  if (L < 1) {  // a rank that owns no limb at this level
+    POST();
+    return 0;
+  }
   const int ch = batch < c->chunk ? batch : c->chunk;
   if ((rc = ws_reserve(c, 4 * (size_t)ch * L * c->N))) return rc;
   for (int b = 0; b < batch; b += ch) {

@@ -56,53 +56,91 @@ def gather_batch(local, total: int, group=None):
 # ------------------------------------------------------------------------------------------------
 # RNS-limb sharding for the largest rings (BASELINE.json configs[3])
 # ------------------------------------------------------------------------------------------------
+def prime_owner(ctx, p: int) -> int:
+    """Group rank that owns ordinary prime `p` (global id) under the limb partition of
+    tiberate/context/rns_partition.py:34-52 as libtb200 applies it (csrc/tb200.cu: tb_group_owner):
+    scale-prime group g (K consecutive primes) -> rank (np - 1 - g) mod world, the base prime -> rank 0."""
+    K = ctx.K
+    ns = ctx.P_global - K - 1
+    np_ = -(-ns // K)
+    return (np_ - 1 - p // K) % ctx.world if p < ns else 0
+
+
 class LimbShardedKeySwitch:
     """Key switch of a polynomial whose limbs are dealt to ranks by digit group
     (tiberate/context/rns_partition.py:34-52; the reference moves the digit states with per-device
     `tensor.to(device)` copies, ckks_engine.py:1248-1265).
 
-    Per call: each rank computes the ModUp digits of the groups it owns (tb200_ks_digits), ONE
-    all-gather completes the digit-state buffer on every rank (its layout is owner-major with equal
-    segments, so the gather is in place and copy-free), then each rank extends / transforms /
-    multiplies / ModDowns its own limbs (tb200_ks_finish).  The special limbs are replicated, as in
-    the reference, so ModDown needs no second exchange.
-    """
+    Per call: each rank computes the ModUp digits of the groups it owns (tb200_ks_digits), ONE all-gather
+    completes the digit-state buffer on every rank (its layout is owner-major with equal segments, so the
+    gather is in place and copy-free), then each rank extends / transforms / multiplies / ModDowns its own
+    limbs.  The special limbs are replicated, as in the reference, so ModDown needs no second exchange.
 
-    def __init__(self, ctx, group=None):
+    overlap=True (default): the all-gather is issued asynchronously and the ModUp of the groups this rank
+    owns (tb200_ks_modup, which=1: extend + forward pass A, ~1/world of a third of the key switch) runs
+    while it is in flight; the other groups' ModUp (which=2) and the core (tb200_ks_core) follow once the
+    digits have arrived.  overlap=False: gather, then tb200_ks_finish."""
+
+    def __init__(self, ctx, group=None, overlap: bool = True):
         import torch.distributed as dist
 
-        self.ctx, self.group = ctx, group
+        self.ctx, self.group, self.overlap = ctx, group, overlap
         self.world = dist.get_world_size(group)
         if ctx.world != self.world or ctx.rank != dist.get_rank(group):
             raise ValueError("context rank/world must match the process group")
         self._state = {}
 
-    def _state_buffer(self, level, like):
+    def _state_buffer(self, level, like, slot=0):
+        """Digit-state buffer, stored [state_rows, (batch,) N]: the rows of one owner are contiguous for the whole
+        batch, so a batched key switch still needs ONE in-place all-gather.  Returns (storage, view handed to the
+        library, segment row0, segment rows); the view is [batch, state_rows, N] with strides (N, batch N, 1)."""
         import torch
 
         S, row0, seg, _ = self.ctx.ks_state_info(level)
-        key = (level, like.device)
+        B = like.shape[0] if like.dim() == 3 else 0
+        key = (level, like.device, slot, B)
         st = self._state.get(key)
         if st is None:
-            st = torch.zeros(S, self.ctx.N, dtype=torch.int64, device=like.device)
+            st = torch.zeros((S, B, self.ctx.N) if B else (S, self.ctx.N), dtype=torch.int64, device=like.device)
             self._state[key] = st
-        return st, row0, seg
+        return st, (st.permute(1, 0, 2) if B else st), row0, seg
 
-    def __call__(self, level: int, a_local, ksk_local, out0, out1, add0=None, add1=None, tail: int = 0):
-        """a_local / out*: this rank's rows [L_local, N] (coefficient domain, canonical);
-        ksk_local: KeySwitchKeyView over the LOCAL key rows ([P_local, N] per digit group)."""
+    def start(self, level: int, a_local, slot: int = 0):
+        """Digits of the owned groups + the all-gather (asynchronous with overlap=True).  Several key switches
+        can be started back to back on different slots: their collectives then run under the ModUp / core
+        kernels of the earlier ones (every rank must start and finish them in the same order)."""
         import torch.distributed as dist
 
-        state, row0, seg = self._state_buffer(level, out0)
-        has_rows = out0.shape[-2] > 0  # deep levels can leave a rank without ordinary limbs
-        if has_rows:
+        store, state, row0, seg = self._state_buffer(level, a_local, slot)
+        if a_local.shape[-2] > 0:  # deep levels can leave a rank without ordinary limbs
             self.ctx.ks_digits(level, a_local, state)
+        work = None
         if self.world > 1:  # every rank takes part, also those that own nothing at this level
-            views = [state[r * seg:(r + 1) * seg] for r in range(self.world)]
-            dist.all_gather(views, state[row0:row0 + seg], group=self.group)
-        if has_rows:
-            self.ctx.ks_finish(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
+            views = [store[r * seg:(r + 1) * seg] for r in range(self.world)]
+            work = dist.all_gather(views, store[row0:row0 + seg], group=self.group, async_op=self.overlap)
+        return state, (work if self.overlap else None)
+
+    def finish(self, level: int, started, ksk_local, out0, out1, add0=None, add1=None, tail: int = 0):
+        ctx = self.ctx
+        state, work = started
+        if out0.shape[-2] == 0:
+            if work is not None:
+                work.wait()
+            return out0, out1
+        if not self.overlap:
+            ctx.ks_finish(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
+            return out0, out1
+        ctx.ks_modup(level, state, which=1)  # own groups: their digits never left this GPU
+        if work is not None:
+            work.wait()  # the compute stream waits for the collective; the host does not block
+        ctx.ks_modup(level, state, which=2)
+        ctx.ks_core(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
         return out0, out1
+
+    def __call__(self, level: int, a_local, ksk_local, out0, out1, add0=None, add1=None, tail: int = 0):
+        """a_local / out*: this rank's rows [L_local, N] or [batch, L_local, N] (coefficient domain, canonical;
+        batch <= the context's chunk); ksk_local: KeySwitchKeyView over the LOCAL key rows ([P_local, N] per group)."""
+        return self.finish(level, self.start(level, a_local), ksk_local, out0, out1, add0, add1, tail)
 
 
 class LimbShardedRescale:
@@ -110,8 +148,9 @@ class LimbShardedRescale:
     dropped limb to the other devices with `tensor.to(device)`, :1560-1575).
 
     The rank that owns prime `level` broadcasts the dropped limb of both polynomials (2 N int64 -- the
-    one exchange of this operation), then every rank rescales the limbs it keeps with the op-layer kernel
-    (tb200_rescale_rows).  Returns this rank's rows at level + 1 (fresh tensors)."""
+    one exchange of this operation; the owner follows from the partition rule, no lookup collective), then
+    every rank rescales the limbs it keeps with the op-layer kernel (tb200_rescale_rows).  Returns this
+    rank's rows at level + 1 (fresh tensors).  The per-level scale tables are built once and cached."""
 
     def __init__(self, ctx, group=None):
         import torch.distributed as dist
@@ -120,6 +159,20 @@ class LimbShardedRescale:
         self.world = dist.get_world_size(group)
         if ctx.world != self.world or ctx.rank != dist.get_rank(group):
             raise ValueError("context rank/world must match the process group")
+        self._scales = {}
+
+    def _scale_table(self, level, kept, device):
+        import torch
+
+        key = (level, str(device))
+        t = self._scales.get(key)
+        if t is None:
+            ctx, R = self.ctx, 1 << 62
+            ql = ctx.q_global[level]
+            t = torch.tensor([(pow(ql, -1, ctx.q_global[g]) * R) % ctx.q_global[g] for g in kept], dtype=torch.int64,
+                             device=device)
+            self._scales[key] = t
+        return t
 
     def __call__(self, level: int, c0_local, c1_local, exact: bool = True):
         import torch
@@ -127,26 +180,69 @@ class LimbShardedRescale:
 
         ctx = self.ctx
         ids = ctx.local_rows(level)
-        owner = level in ids
-        drop = torch.zeros(2, ctx.N, dtype=torch.int64, device=c0_local.device)
+        owner_rank = prime_owner(ctx, level)
+        owner = owner_rank == ctx.rank
+        assert owner == (level in ids)
+        drop = torch.empty(2, ctx.N, dtype=torch.int64, device=c0_local.device)
         if owner:  # the dropped prime is the smallest alive id: local row 0
             drop[0].copy_(c0_local[0])
             drop[1].copy_(c1_local[0])
         if self.world > 1:
-            who = torch.tensor([ctx.rank if owner else -1], dtype=torch.int64, device=c0_local.device)
-            dist.all_reduce(who, op=dist.ReduceOp.MAX, group=self.group)
-            dist.broadcast(drop, src=int(who.item()), group=self.group)
+            src = dist.get_global_rank(self.group, owner_rank) if self.group is not None else owner_rank
+            dist.broadcast(drop, src=src, group=self.group)
         kept = [g for g in ids if g > level]
         outs = []
         for i, c in enumerate((c0_local, c1_local)):
             out = (c[1:] if owner else c).clone()
             if kept:
-                ql, R = ctx.q_global[level], 1 << 62
-                scales = torch.tensor([(pow(ql, -1, ctx.q_global[g]) * R) % ctx.q_global[g] for g in kept],
-                                      dtype=torch.int64, device=c.device)
-                ctx.rescale_rows(out, ctx.local_prime_ids.index(kept[0]), scales, drop[i], ql // 2, exact)
+                ctx.rescale_rows(out, ctx.local_prime_ids.index(kept[0]), self._scale_table(level, kept, c.device),
+                                 drop[i], ctx.q_global[level] // 2, exact)
             outs.append(out)
         return outs[0], outs[1]
+
+
+class LimbShardedOps:
+    """Whole homomorphic operations on limb-sharded ciphertexts (BASELINE.json configs[3]): every step other
+    than the two exchanges above is limb-local and runs on this rank's rows only.
+
+      rotate(level, galois, c0, c1, rotk)      tiberate/ckks_engine.py:1804-1840: automorphism (local) +
+                                                key switch of the rotated c1 with the switch-key tail
+      cc_mult_relin(level, a, b, evk)           :1640-1732: rescale both operands (one broadcast each), tensor
+                                                product in the NTT domain (local), inverse transforms (local),
+                                                key switch of d2 with the relinearisation tail
+    Results are this rank's rows of the reference's result, bit for bit (tests/test_dist_gloo.py,
+    tests/test_gpu_sharded.py)."""
+
+    def __init__(self, ctx, group=None, overlap: bool = True):
+        self.ctx = ctx
+        self.ks = LimbShardedKeySwitch(ctx, group, overlap)
+        self.rs = LimbShardedRescale(ctx, group)
+
+    def rotate(self, level: int, galois: int, c0, c1, rotk_local):
+        import torch
+
+        r0, r1 = torch.empty_like(c0), torch.empty_like(c1)
+        self.ctx.rotate(level, galois, c0, c1, None, r0, r1)  # automorphism only: limb-local
+        o0, o1 = torch.empty_like(c0), torch.empty_like(c1)
+        self.ks(level, r1, rotk_local, o0, o1, add0=r0, tail=2)
+        return o0, o1
+
+    def cc_mult_relin(self, level: int, a0, a1, b0, b1, evk_local):
+        import torch
+
+        ctx = self.ctx
+        x0, x1 = self.rs(level, a0, a1)
+        y0, y1 = (x0, x1) if (a0 is b0 and a1 is b1) else self.rs(level, b0, b1)
+        lvl = level + 1
+        d = [torch.empty_like(x0) for _ in range(3)]
+        if x0.shape[-2] > 0:
+            ctx.cc_mult_triplet(lvl, x0, x1, y0, y1, d[0], d[1], d[2], False)
+            p0 = ctx.local_prime_ids.index(ctx.local_rows(lvl)[0])
+            for t in d:  # intt_radix2_exit_reduce (ckks_engine.py:1709-1711)
+                ctx.intt(t, p0, 2)
+        o0, o1 = torch.empty_like(x0), torch.empty_like(x1)
+        self.ks(lvl, d[2], evk_local, o0, o1, add0=d[0], add1=d[1], tail=1)
+        return o0, o1
 
 
 def shard_rows(t, ctx, level: int, with_special: bool = False):
