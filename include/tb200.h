@@ -95,8 +95,12 @@ int tb200_ctx_set_f64_share(tb200_ctx*, int eighths);
  *     joined again, beside the launches over the FP64 limb rows; 0: one stream.
  *   TB200_TUNE_FUSED_MODDOWN (default 0: measured 63 us against 36 + 20 us separately, B200 logN16): ModDown and the relinearisation / switch-key tail run inside the
  *     exit of inverse pass A of the ordinary limbs (after the special limbs were transformed and
- *     chain-reduced); 0: separate kernels over the coefficient-domain sums. */
-enum tb200_tuning { TB200_TUNE_FUSED_CORE = 0, TB200_TUNE_SIDE_ROWS = 1, TB200_TUNE_FUSED_MODDOWN = 2 };
+ *     chain-reduced); 0: separate kernels over the coefficient-domain sums.
+ *   TB200_TUNE_STREAM_WS (default 1): the scratch of an engine call is leased from the device's stream-ordered
+ *     memory pool on the caller's stream (see "Streams, threads and CUDA graphs" below); 0: one grow-only
+ *     workspace per context (single stream, growth synchronises the device). */
+enum tb200_tuning { TB200_TUNE_FUSED_CORE = 0, TB200_TUNE_SIDE_ROWS = 1, TB200_TUNE_FUSED_MODDOWN = 2,
+                    TB200_TUNE_STREAM_WS = 3 };
 int tb200_ctx_set_tuning(tb200_ctx*, int knob, int value);
 
 /* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/tb200.h"
@@ -33,6 +34,7 @@ struct ProfRec {
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;  // launches may come from several host threads
 #ifndef TB200_HOST_EMU
 #define PROF_BEGIN(name_, stream)                                 \
   ProfRec pr_;                                                    \
@@ -45,6 +47,7 @@ static std::vector<ProfRec> g_prof;
 #define PROF_END(stream)                             \
   if (g_prof_on) {                                   \
     cudaEventRecord(pr_.e1, (cudaStream_t)(stream)); \
+    std::lock_guard<std::mutex> lk_(g_prof_mu);      \
     g_prof.push_back(pr_);                           \
   }
 #else
@@ -71,6 +74,26 @@ static std::vector<ProfRec> g_prof;
     cudaError_t e_ = cudaPeekAtLastError();                                        \
     if (e_ != cudaSuccess) return fail((int)e_, "launch: %s", cudaGetErrorString(e_)); \
   } while (0)
+
+// cudaSetDevice for the duration of one entry point; the caller's current device is restored on return
+// (the reference's launchers leave it changed).
+struct DevGuard {
+  int prev = -1;
+  cudaError_t set(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev == dev) {
+      prev = -1;
+      return cudaSuccess;
+    }
+    return cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define SET_DEVICE(dev) \
+  DevGuard dev_guard_;  \
+  CK(dev_guard_.set(dev))
 
 extern "C" const char* tb200_last_error(void) { return g_err; }
 extern "C" const char* tb200_version(void) { return "tb200 0.1 (sm_100a)"; }
@@ -191,6 +214,16 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
     fail(TB200_ENODEV, "ctx_create: cudaSetDevice(%d) failed", device);
     return nullptr;
   }
+#ifndef TB200_HOST_EMU
+  {  // keep freed workspace blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
+#endif
   tb200_ctx* c = new tb200_ctx();
   c->device = device;
   c->logN = logN;
@@ -514,7 +547,7 @@ extern "C" int tb200_ctx_set_fast(tb200_ctx* c, int on) {
 // stay on the integer pipes, so co-resident CTAs of both kinds keep both pipes busy.
 extern "C" int tb200_ctx_set_f64_share(tb200_ctx* c, int eighths) {
   if (!c || eighths < 0 || eighths > 8) return fail(TB200_EINVAL, "f64 share must be 0..8 (eighths)");
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   c->f64_eighths = eighths;
   for (int g = 0; g < c->P; ++g) c->fps[g].f64 = (c->fps[g].small && ((g * 5) & 7) < eighths) ? 1 : 0;
   CK(cudaDeviceSynchronize());
@@ -534,6 +567,9 @@ extern "C" int tb200_ctx_set_tuning(tb200_ctx* c, int knob, int value) {
     case TB200_TUNE_FUSED_MODDOWN:
       c->fused_moddown = value != 0;
       return 0;
+    case TB200_TUNE_STREAM_WS:
+      c->stream_ws = value != 0;
+      return 0;
   }
   return fail(TB200_EINVAL, "unknown tuning knob %d", knob);
 }
@@ -552,6 +588,39 @@ static int ws_reserve(tb200_ctx* c, size_t elems) {
   c->ws_elems = elems;
   return 0;
 }
+
+// Scratch of one engine call.  Default: leased from the device's stream-ordered memory pool on the CALLER'S
+// stream (cudaMallocAsync at entry, cudaFreeAsync at exit): calls issued on different streams or from
+// different host threads get different blocks, nothing synchronises the device, and the whole call is a
+// sequence of stream operations that a CUDA graph can capture.  TB200_TUNE_STREAM_WS = 0 selects the
+// grow-only workspace owned by the context (one stream at a time; growth synchronises the device).
+struct WsLease {
+  tb200_ctx* c;
+  cudaStream_t st;
+  i64* p = nullptr;
+  bool leased = false;
+  WsLease(tb200_ctx* c_, tb200_stream st_) : c(c_), st((cudaStream_t)st_) {}
+  WsLease(const WsLease&) = delete;
+  WsLease& operator=(const WsLease&) = delete;
+  int reserve(size_t elems) {
+    if (!c->stream_ws) {
+      int rc = ws_reserve(c, elems);
+      p = c->ws;
+      return rc;
+    }
+    if (cudaMallocAsync((void**)&p, (elems ? elems : 1) * sizeof(i64), st) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      return fail(TB200_ENOMEM, "workspace of %zu MiB could not be allocated", elems * 8 >> 20);
+    }
+    leased = true;
+    return 0;
+  }
+  ~WsLease() {
+    if (leased && p) cudaFreeAsync(p, st);
+  }
+};
+
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -626,7 +695,7 @@ extern "C" int tb200_pointwise(tb200_ctx* c, int op, int rows, int batch, int pr
   if (explicit_c && needs_k && !(ec->kl && ec->kh) ) return fail(TB200_EINVAL, "op %d needs kl/kh", op);
   if (explicit_c && (op == 6 || op == 7 || op == 13))
     return fail(TB200_EINVAL, "op %d takes its constants from the context only", op);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   TbPwArgs g;
   g.a = view(a);
   g.b = has_b ? view(b) : view(a);
@@ -656,7 +725,7 @@ extern "C" int tb200_add_many(tb200_ctx* c, int pairwise, int K, int rows, int p
                               int64_t* out, tb200_stream st) {
   if (!c || !in || !out || K < 1) return fail(TB200_EINVAL, "add_many: bad arguments");
   CHECK_ROWS(prime0, rows);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   LAUNCH(k_add_many, grid_pw(c, rows, 1, 1), dim3(256), st, c->dev(), (const i64*)in, (i64*)out, K, rows, c->N,
          prime0, pairwise);
   POST();
@@ -757,7 +826,7 @@ extern "C" int tb200_ntt(tb200_ctx* c, int rows, int batch, int prime0, const tb
   CHECK_ROWS(prime0, rows);
   CHECK_POLY(a);
   if (batch < 1) return fail(TB200_EINVAL, "batch must be >= 1");
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   int rc = ntt_forward(c, view(a), view(a), rows, batch, prime0, enter != 0, st);
   if (rc) return rc;
   POST();
@@ -774,7 +843,7 @@ extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const t
   CHECK_ROWS(prime0, rows);
   CHECK_POLY(a);
   if (batch < 1 || mode < 0 || mode > 3) return fail(TB200_EINVAL, "bad batch/mode");
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   // intt_radix2_exit_reduce returns canonical residues, so the mod-q transforms give the same bits
   // (domain: |x| < 2^51 on the FP64 limbs, (-2q, 2q) elsewhere -- every lazy value the ops produce;
   // tb200_ctx_set_fast(ctx, 0) selects the reference's own butterflies for anything wider)
@@ -998,7 +1067,7 @@ extern "C" int tb200_rescale_rows(tb200_ctx* c, int rows, int prime0, const tb20
   CHECK_ROWS(prime0, rows);
   CHECK_POLY(a);
   if (((uintptr_t)rescaler & 15) != 0) return fail(TB200_EINVAL, "rescaler must be 16-byte aligned");
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   TbView r;
   r.p = (i64*)rescaler;
   r.bs = 0;
@@ -1014,7 +1083,7 @@ extern "C" int tb200_extend(tb200_ctx* c, int rows, int prime0, int alpha, const
                             int64_t out_stride, tb200_stream st) {
   if (!c || !state || !out || alpha < 1 || (alpha > 1 && !l_enter)) return fail(TB200_EINVAL, "extend: bad arguments");
   CHECK_ROWS(prime0, rows);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   LAUNCH(k_extend_op, grid_pw(c, rows, 1, 1), dim3(256), st, c->dev(), (const i64*)state, (long)state_stride, alpha,
          (const i64*)l_enter, (long)le_stride, (long)le_off, (i64*)out, (long)out_stride, prime0, c->N);
   POST();
@@ -1027,7 +1096,7 @@ extern "C" int tb200_codec_rotate(tb200_ctx* c, int rows, const tb200_poly* a, c
   CHECK_POLY(a);
   CHECK_POLY(out);
   if (a->ptr == out->ptr) return fail(TB200_EINVAL, "codec_rotate cannot run in place");
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   LAUNCH(k_codec_rotate_op, grid_pw(c, rows, 1, 1), dim3(256), st, view(a), (const i64*)perm, (const i64*)two_q,
          view(out), c->N);
   POST();
@@ -1069,7 +1138,7 @@ extern "C" int tb200_divide_by_p(tb200_ctx* c, int level, const tb200_poly* cc, 
   CHECK_POLY(cc);
   CHECK_POLY(p);
   CHECK_POLY(out);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   int rc = moddown(c, level, 1, view(cc), view(p), view(cc), view(out), 0, st);
   if (rc) return rc;
   POST();
@@ -1111,7 +1180,7 @@ extern "C" int tb200_rescale(tb200_ctx* c, int level, int batch, const tb200_pol
   if (level + 1 >= c->num_ord) return fail(TB200_EINVAL, "rescale: level %d is the last level", level);
   CHECK_POLY(in0);
   CHECK_POLY(out0);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   rescale_impl(c, level, batch, view(in0), view(out0), exact, st);
   if (in1) {
     CHECK_POLY(in1);
@@ -1341,7 +1410,7 @@ extern "C" int tb200_ks_digits(tb200_ctx* c, int level, int batch, const tb200_p
   if (rc) return rc;
   if (c->ks[level].nown > 0) CHECK_POLY(a);
   CHECK_POLY(state);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   if ((rc = ks_digits(c, level, batch, view(a), view(state), st))) return rc;
   POST();
   return 0;
@@ -1359,13 +1428,14 @@ extern "C" int tb200_ks_finish(tb200_ctx* c, int level, int batch, const tb200_p
   if (tail == 1) CHECK_POLY(add1);
   TbKskDev key;
   if ((rc = make_key(c, level, ksk, &key))) return rc;
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * ch))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve(ks_ws_elems(c, level) * ch))) return rc;
   for (int b0 = 0; b0 < batch; b0 += ch) {
     const int nb = batch - b0 < ch ? batch - b0 : ch;
     rc = ks_finish(c, level, nb, shift(view(state), b0), key, shift(view(add0 ? add0 : out0), b0),
-                   shift(view(add1 ? add1 : out1), b0), shift(view(out0), b0), shift(view(out1), b0), tail, c->ws, st);
+                   shift(view(add1 ? add1 : out1), b0), shift(view(out0), b0), shift(view(out1), b0), tail, ws.p, st);
     if (rc) return rc;
   }
   POST();
@@ -1381,7 +1451,7 @@ extern "C" int tb200_ks_modup(tb200_ctx* c, int level, int batch, const tb200_po
   if (which < 0 || which > 2) return fail(TB200_EINVAL, "ks_modup: which must be 0 (all), 1 (own) or 2 (foreign)");
   if (batch > c->chunk) return fail(TB200_EINVAL, "ks_modup: batch %d exceeds the chunk %d", batch, c->chunk);
   CHECK_POLY(state);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   if ((rc = ws_reserve(c, ks_ws_elems(c, level) * (size_t)batch))) return rc;
   if ((rc = ks_modup(c, level, batch, view(state), c->ws, st, false, which))) return rc;
   POST();
@@ -1401,7 +1471,7 @@ extern "C" int tb200_ks_core(tb200_ctx* c, int level, int batch, const tb200_pol
   if (tail == 1) CHECK_POLY(add1);
   TbKskDev key;
   if ((rc = make_key(c, level, ksk, &key))) return rc;
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   if (c->ws_elems < ks_ws_elems(c, level) * (size_t)batch) return fail(TB200_EINVAL, "ks_core: call tb200_ks_modup first");
   rc = ks_finish(c, level, batch, view(state), key, view(add0 ? add0 : out0), view(add1 ? add1 : out1), view(out0),
                  view(out1), tail, c->ws, st, nullptr, true);
@@ -1420,13 +1490,14 @@ extern "C" int tb200_keyswitch(tb200_ctx* c, int level, int batch, const tb200_p
   CHECK_POLY(out1);
   TbKskDev key;
   if ((rc = make_key(c, level, ksk, &key))) return rc;
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * ch))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve(ks_ws_elems(c, level) * ch))) return rc;
   for (int b0 = 0; b0 < batch; b0 += ch) {
     const int nb = batch - b0 < ch ? batch - b0 : ch;
     rc = keyswitch_chunk(c, level, nb, shift(view(a), b0), key, shift(view(a), b0), shift(view(a), b0),
-                         shift(view(out0), b0), shift(view(out1), b0), 0, c->ws, st);
+                         shift(view(out0), b0), shift(view(out1), b0), 0, ws.p, st);
     if (rc) return rc;
   }
   POST();
@@ -1445,13 +1516,14 @@ extern "C" int tb200_switch_key(tb200_ctx* c, int level, int batch, const tb200_
   CHECK_POLY(out1);
   TbKskDev key;
   if ((rc = make_key(c, level, ksk, &key))) return rc;
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, ks_ws_elems(c, level) * ch))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve(ks_ws_elems(c, level) * ch))) return rc;
   for (int b0 = 0; b0 < batch; b0 += ch) {
     const int nb = batch - b0 < ch ? batch - b0 : ch;
     rc = keyswitch_chunk(c, level, nb, shift(view(c1), b0), key, shift(view(c0), b0), shift(view(c0), b0),
-                         shift(view(out0), b0), shift(view(out1), b0), 2, c->ws, st);
+                         shift(view(out0), b0), shift(view(out1), b0), 2, ws.p, st);
     if (rc) return rc;
   }
   POST();
@@ -1471,7 +1543,7 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
   if (!(galois & 1) || galois < 1 || galois >= 2 * (int64_t)c->N)
     return fail(TB200_EINVAL, "galois element must be odd and in [1, 2N)");
   if (c0->ptr == out0->ptr || c1->ptr == out1->ptr) return fail(TB200_EINVAL, "rotate cannot run in place");
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int N = c->N, L = c->num_ord - c->lstart[level];
   if (!rotk) {
     if (L > 0) {
@@ -1486,10 +1558,11 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
   if ((rc = make_key(c, level, rotk, &key))) return rc;
   const int ch = batch < c->chunk ? batch : c->chunk;
   const size_t rot_elems = 2 * (size_t)L * N;  // rotated c0, c1 per ciphertext
-  if ((rc = ws_reserve(c, (ks_ws_elems(c, level) + rot_elems) * ch))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve((ks_ws_elems(c, level) + rot_elems) * ch))) return rc;
   for (int b0 = 0; b0 < batch; b0 += ch) {
     const int nb = batch - b0 < ch ? batch - b0 : ch;
-    i64* r0 = c->ws;
+    i64* r0 = ws.p;
     i64* r1 = r0 + (size_t)nb * L * N;
     i64* ksws = r1 + (size_t)nb * L * N;
     const dim3 gridb((unsigned)((N + 255) / 256), (unsigned)L, (unsigned)nb);
@@ -1549,18 +1622,19 @@ extern "C" int tb200_cc_mult_triplet(tb200_ctx* c, int level, int batch, const t
   CHECK_POLY(d0);
   CHECK_POLY(d1);
   CHECK_POLY(d2);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int lvl = level + (pre_rescale ? 1 : 0), L = c->num_ord - c->lstart[lvl];
   if (L < 1) {  // a rank that owns no limb at this level
     POST();
     return 0;
   }
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, 4 * (size_t)ch * L * c->N))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve(4 * (size_t)ch * L * c->N))) return rc;
   for (int b = 0; b < batch; b += ch) {
     const int nb = batch - b < ch ? batch - b : ch;
     rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
-                    pre_rescale, c->ws, shift(view(d0), b), shift(view(d1), b), shift(view(d2), b), false, st);
+                    pre_rescale, ws.p, shift(view(d0), b), shift(view(d1), b), shift(view(d2), b), false, st);
     if (rc) return rc;
   }
   POST();
@@ -1612,14 +1686,15 @@ extern "C" int tb200_relinearize(tb200_ctx* c, int level, int batch, const tb200
   CHECK_POLY(out1);
   TbKskDev key;
   if ((rc = make_key(c, level, evk, &key))) return rc;
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int N = c->N, L = c->num_ord - level;
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, (4 * (size_t)L * N + ks_ws_elems(c, level)) * ch))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve((4 * (size_t)L * N + ks_ws_elems(c, level)) * ch))) return rc;
   for (int b = 0; b < batch; b += ch) {
     const int nb = batch - b < ch ? batch - b : ch;
     const size_t pe = (size_t)nb * L * N;
-    i64* d = c->ws;
+    i64* d = ws.p;
     const tb200_poly* src[3] = {d0, d1, d2};
     for (int i = 0; i < 3; ++i) {  // copy (the reference mutates its triplet; we do not)
       TbPwArgs g;
@@ -1654,15 +1729,16 @@ extern "C" int tb200_cc_mult_relin(tb200_ctx* c, int level, int batch, const tb2
   const int lvl = level + (pre_rescale ? 1 : 0);
   TbKskDev key;
   if ((rc = make_key(c, lvl, evk, &key))) return rc;
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int N = c->N, L = c->num_ord - lvl;
   const int ch = batch < c->chunk ? batch : c->chunk;
   // workspace: x[4] | d[3] | key-switch
-  if ((rc = ws_reserve(c, (7 * (size_t)L * N + ks_ws_elems(c, lvl)) * ch))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve((7 * (size_t)L * N + ks_ws_elems(c, lvl)) * ch))) return rc;
   for (int b = 0; b < batch; b += ch) {
     const int nb = batch - b < ch ? batch - b : ch;
     const size_t pe = (size_t)nb * L * N;
-    i64* x = c->ws;
+    i64* x = ws.p;
     i64* d = x + 4 * pe;
     i64* ksws = d + 3 * pe;
     rc = mult_front(c, level, nb, shift(view(a0), b), shift(view(a1), b), shift(view(b0), b), shift(view(b1), b),
@@ -1687,17 +1763,18 @@ extern "C" int tb200_pc_mult(tb200_ctx* c, int level, int batch, const tb200_pol
   CHECK_POLY(c1);
   CHECK_POLY(out0);
   CHECK_POLY(out1);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int N = c->N, L = c->num_ord - level;
   const int ch = batch < c->chunk ? batch : c->chunk;
-  if ((rc = ws_reserve(c, 2 * (size_t)ch * L * N))) return rc;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve(2 * (size_t)ch * L * N))) return rc;
   for (int b = 0; b < batch; b += ch) {
     const int nb = batch - b < ch ? batch - b : ch;
     const size_t pe = (size_t)nb * L * N;
     const tb200_poly* in[2] = {c0, c1};
     const tb200_poly* out[2] = {out0, out1};
     for (int h = 0; h < 2; ++h) {
-      TbView x = dense(c->ws + h * pe, L, N);
+      TbView x = dense(ws.p + h * pe, L, N);
       rc = c->fast ? fast_forward_enter(c, shift(view(in[h]), b), x, L, nb, level, -1, st)
                    : ntt_forward(c, shift(view(in[h]), b), x, L, nb, level, true, st);
       if (rc) return rc;
@@ -1733,7 +1810,7 @@ extern "C" int tb200_cc_addsub(tb200_ctx* c, int level, int batch, int sub, cons
   CHECK_POLY(b1);
   CHECK_POLY(out0);
   CHECK_POLY(out1);
-  CK(cudaSetDevice(c->device));
+  SET_DEVICE(c->device);
   const int L = c->num_ord - level;
   const tb200_poly* A[2] = {a0, a1};
   const tb200_poly* B[2] = {b0, b1};
@@ -1765,7 +1842,7 @@ static int rng_table(TbRngTable* t, const uint64_t* host, int n, const char* wha
 #define RNG_ENTER(ptr, cnt, what)                                                                 \
   if (!(ptr) || (cnt) < 1) return fail(TB200_EINVAL, what ": null buffer or empty");               \
   if (((uintptr_t)(ptr)&15) != 0) return fail(TB200_EINVAL, what ": buffers must be 16-byte aligned"); \
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
 
 extern "C" int tb200_chacha20(int device, int64_t* states, int64_t n_rows, int64_t* out, int64_t step, tb200_stream st) {
   RNG_ENTER(states, n_rows, "chacha20");
@@ -1825,7 +1902,7 @@ extern "C" int tb200_discrete_gaussian(int device, int64_t* words, int64_t n_row
 }
 extern "C" int tb200_randround(int device, const double* coef, int64_t* words, int64_t n, tb200_stream st) {
   if (!coef || !words || n < 1) return fail(TB200_EINVAL, "randround: null buffer or empty");
-  CK(cudaSetDevice(device));
+  SET_DEVICE(device);
   LAUNCH(k_rng_randround, dim3((unsigned)((n + 255) / 256)), dim3(256), st, coef, (i64*)words, (long)n);
   POST();
   return 0;

@@ -116,6 +116,8 @@ static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t
   std::memset(d, v, n);
   return 0;
 }
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 typedef void* cudaEvent_t;
 #define cudaStreamNonBlocking 1
 #define cudaEventDisableTiming 2
