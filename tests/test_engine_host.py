@@ -59,3 +59,45 @@ def test_loading_never_unpickles_arbitrary_objects(tmp_path):
         pickle.dump({"format": "tb200-datastruct-1", "payload": Evil()}, f)
     with pytest.raises(Exception):
         DataStruct.load(p)
+
+
+def test_reference_pickles_load_without_executing_code(tmp_path):
+    """files written by the reference's DataStruct.save (pickle of its own classes,
+    tiberate/typing.py:283-290; fixtures made by tests/golden/make_ref_pickles.py from /root/reference) are read
+    through an allow-list unpickler into this package's classes; anything else in the stream is refused."""
+    import os
+    import pickle
+
+    import pytest
+    import torch
+
+    from tiberate_fhe_b200 import typing as T
+
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    want = torch.load(os.path.join(g, "ref_pickles_expected.pt"), weights_only=True)
+    ct = T.load_reference_pickle(os.path.join(g, "ref_ciphertext.pkl"))
+    assert type(ct) is T.Ciphertext and ct.level == 2 and ct.misc["logN"] == 4 and ct.misc["note"] == "from the reference"
+    assert ct.misc["absent"] is None and not ct.has_flag(T.FLAGS.NTT_STATE)
+    assert torch.equal(ct.data[0][0], want["ct"][0]) and torch.equal(ct.data[1][0], want["ct"][1])
+    rk = T.load_reference_pickle(os.path.join(g, "ref_rotation_key.pkl"))
+    assert type(rk) is T.RotationKey and rk.delta == 3 and len(rk.data) == 2
+    assert rk.has_flag(T.FLAGS.INCLUDE_SPECIAL) and rk.has_flag(T.FLAGS.NTT_STATE) and rk.has_flag(T.FLAGS.MONTGOMERY_STATE)
+    for part, (b, a) in zip(rk.data, want["rk"]):
+        assert type(part) is T.PublicKey and torch.equal(part.data[0][0], b) and torch.equal(part.data[1][0], a)
+    # round trip into the package's own (pickle-free) format
+    p = tmp_path / "ct.tb200"
+    ct.save(str(p))
+    assert torch.equal(T.Ciphertext.load(str(p)).data[1][0], want["ct"][1])
+
+    class Evil:
+        def __reduce__(self):
+            import os as _os
+
+            return (_os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    bad = tmp_path / "evil.pkl"
+    with open(bad, "wb") as f:
+        pickle.dump(Evil(), f)
+    with pytest.raises(pickle.UnpicklingError):
+        T.load_reference_pickle(str(bad))
+    assert not (tmp_path / "pwned").exists()

@@ -177,15 +177,10 @@ __device__ __noinline__ double exact_enter_cold(i64 x, i64 Rs, u64 q4, u64 k) {
 // CTA-uniform: may this tile take ExactF64Pol?  (prime on the FP64 pipe and every residue below 2^50 in magnitude)
 __device__ __forceinline__ bool tile_fits_f64(const TbDev& c, int g, const i64 (&x)[16]) {
   if (!c.x64 || !c.fp[g].f64) return false;
-  TB_KERNEL_SHARED int wide;
-  if (threadIdx.x == 0) wide = 0;
-  __syncthreads();
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < 16; ++i) bad |= (x[i] >= (1ll << 50)) | (x[i] <= -(1ll << 50));
-  if (bad) wide = 1;
-  __syncthreads();
-  return wide == 0;
+  return !tb_block_any(bad);  // barrier + OR over the CTA (no shared flag written by several threads)
 }
 __device__ __forceinline__ tb::ExactF64Pol exact_f64_policy(const TbDev& c, int g, const tb::PrimeRegs& p, const u64* psi4) {
   const TbFastPrime& F = c.fp[g];

@@ -19,6 +19,7 @@
 #define TB_SET_MAX_DYN_SMEM(kernel, bytes) \
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 static __device__ __forceinline__ double tb_rint(double a) { return rint(a); }
+static __device__ __forceinline__ bool tb_block_any(bool pred) { return __syncthreads_or(pred ? 1 : 0) != 0; }
 // streaming (L2-only) accesses for data that is touched once per kernel
 static __device__ __forceinline__ long tb_ldcg(const long* p) { return __ldcg(p); }
 static __device__ __forceinline__ longlong2 tb_ldcg2(const longlong2* p) { return __ldcg(p); }
@@ -52,6 +53,17 @@ void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body);
 #define TB_KERNEL_SHARED static
 #define TB_SET_MAX_DYN_SMEM(kernel, bytes) ((void)0)
 #define __syncthreads() emu_syncthreads()
+#include <atomic>
+static inline bool tb_block_any(bool pred) {
+  static std::atomic<int> flag{0};
+  if (threadIdx.x == 0) flag.store(0);
+  emu_syncthreads();
+  if (pred) flag.store(1);
+  emu_syncthreads();
+  const bool r = flag.load() != 0;
+  emu_syncthreads();
+  return r;
+}
 template <class T>
 static inline T __ldg(const T* p) {
   return *p;

@@ -186,3 +186,84 @@ class ConjugationKey(DataStruct):
 
 _CLASSES = {c.__name__: c for c in (Ciphertext, CiphertextTriplet, SecretKey, EvaluationKey, PublicKey, KeySwitchKey,
                                     RotationKey, ConjugationKey)}
+
+
+# ---- reading files written by the reference ------------------------------------------
+# The reference saves a DataStruct with pickle.dump(self) (tiberate/typing.py:283-290).  Loading such a
+# file with pickle.load would execute whatever the file says; this loader accepts exactly what a genuine
+# file contains and nothing else: the tiberate.typing classes (mapped onto the classes of this module),
+# defaultdict / OrderedDict, torch's tensor rebuild helpers, numpy array reconstruction, and the storage
+# loader -- re-implemented on top of torch.load(weights_only=True).  Any other global raises UnpicklingError.
+_REF_TYPING = {"Ciphertext": Ciphertext, "CiphertextTriplet": CiphertextTriplet, "Plaintext": Plaintext,
+               "SecretKey": SecretKey, "EvaluationKey": EvaluationKey, "PublicKey": PublicKey,
+               "KeySwitchKey": KeySwitchKey, "RotationKey": RotationKey, "GaloisKey": KeySwitchKey,
+               "ConjugationKey": ConjugationKey, "DataStruct": DataStruct, "FLAGS": FLAGS, "_default_none": _none}
+
+
+class _RefCachedDict(dict):
+    """Stands in for vdtoys.cache.CachedDict (a dict with a generator function): only the stored items survive."""
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            inner = state.get("_cache")
+            if isinstance(inner, dict):
+                self.update(inner)
+
+
+def load_reference_pickle(path: str, map_location=None):
+    """Ciphertext / key / plaintext file written by tiberate's DataStruct.save -> the matching class of this
+    module (same `data` nesting, flags, level, misc), without executing code from the file."""
+    import io
+    import pickle
+
+    import torch
+
+    def safe_storage_from_bytes(b):
+        return torch.load(io.BytesIO(b), weights_only=True, map_location=map_location)
+
+    allowed = {
+        ("collections", "defaultdict"): defaultdict,
+        ("collections", "OrderedDict"): __import__("collections").OrderedDict,
+        ("torch._utils", "_rebuild_tensor_v2"): torch._utils._rebuild_tensor_v2,
+        ("torch._utils", "_rebuild_parameter"): torch._utils._rebuild_parameter,
+        ("torch.storage", "_load_from_bytes"): safe_storage_from_bytes,
+        ("torch", "device"): torch.device,
+        ("torch", "Size"): torch.Size,
+        ("vdtoys.cache", "CachedDict"): _RefCachedDict,
+    }
+    for name in ("int64", "int32", "float64", "float32", "complex128", "complex64", "bool", "uint8"):
+        allowed[("torch", name)] = getattr(torch, name)
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module == "tiberate.typing" and name in _REF_TYPING:
+                return _REF_TYPING[name]
+            if (module, name) in allowed:
+                return allowed[(module, name)]
+            if module in ("numpy.core.multiarray", "numpy._core.multiarray") and name in ("_reconstruct", "scalar"):
+                import numpy.core.multiarray as m
+
+                return getattr(m, name)
+            if module == "numpy" and name in ("ndarray", "dtype"):
+                import numpy
+
+                return getattr(numpy, name)
+            raise pickle.UnpicklingError(f"{path}: global {module}.{name} is not part of a tiberate data file")
+
+    with open(path, "rb") as f:
+        obj = Unpickler(f).load()
+    if not isinstance(obj, DataStruct):
+        raise pickle.UnpicklingError(f"{path} does not hold a tiberate data structure")
+
+    def move(x):
+        if isinstance(x, torch.Tensor):
+            return x.to(map_location) if map_location is not None else x
+        if isinstance(x, list):
+            return [move(y) for y in x]
+        if isinstance(x, DataStruct):
+            x.data = move(x.data)
+        return x
+
+    if not isinstance(getattr(obj, "misc", None), defaultdict):
+        obj.misc = defaultdict(_none, getattr(obj, "misc", None) or {})
+    return move(obj)
