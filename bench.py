@@ -318,8 +318,10 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "avg_launch_ms": tms / nl, "launches_per_step": nl // psteps,
-                "note": "algorithmic limb passes of this kernel class per HMult x N x 8 B (DESIGN.md 4); ncu: FP64 pipe "
-                        "39 %, ALU 44 %, issue slots 58 % busy -- co-limited by instruction issue and HBM, see DESIGN.md 6"}
+                "note": "algorithmic limb passes of this kernel class per HMult x N x 8 B (DESIGN.md 4); the binding "
+                        "resource of every transform kernel is FP64 instruction issue (an FP64 warp instruction holds the "
+                        "SM sub-partition's issue port for 2 cycles and integer instructions do not overlap it: "
+                        "tools/ubench_fp64.cu, profiles/r02_ubench_fp64.txt), not HBM -- see DESIGN.md 6"}
     elif top is not None:
         nl, tms = kern[top]
         roof = {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
@@ -348,7 +350,7 @@ def run_ours(args):
     dout = [[out0[k * sb:(k + 1) * sb], out1[k * sb:(k + 1) * sb]] for k in range(2)]  # two output slots
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
-    def e2e_step():
+    def e2e_step(compute=True):
         ev_cmp, ev_out = [None, None], [None, None]
         for i in range(nsub):
             k = i % 2
@@ -363,7 +365,8 @@ def run_ours(args):
                 s_cmp.wait_event(ev_in)
                 if ev_out[k] is not None:
                     s_cmp.wait_event(ev_out[k])         # slot's previous outputs copied out
-                ctx.cc_mult_relin(0, din[k][0], din[k][1], din[k][2], din[k][3], evk, dout[k][0], dout[k][1], True)
+                if compute:
+                    ctx.cc_mult_relin(0, din[k][0], din[k][1], din[k][2], din[k][3], evk, dout[k][0], dout[k][1], True)
                 ev_cmp[k] = torch.cuda.Event()
                 ev_cmp[k].record(s_cmp)
             with torch.cuda.stream(s_out):
@@ -373,17 +376,17 @@ def run_ours(args):
                 ev_out[k] = torch.cuda.Event()
                 ev_out[k].record(s_out)
 
-    def e2e_timed(steps, warmup):
+    def e2e_timed(steps, warmup, compute=True):
         cur = torch.cuda.current_stream()
         for _ in range(warmup):
-            e2e_step()
+            e2e_step(compute)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(cur)
         for st_ in (s_in, s_cmp, s_out):
             st_.wait_event(e0)
         for _ in range(steps):
-            e2e_step()
+            e2e_step(compute)
         for st_ in (s_in, s_cmp, s_out):
             ev = torch.cuda.Event()
             ev.record(st_)
@@ -398,11 +401,15 @@ def run_ours(args):
         return ms_
 
     ms_e2e = e2e_timed(args.steps, 1)
+    ms_copy = e2e_timed(args.steps, 1, compute=False)  # the same pipeline without the kernels: the host / PCIe ceiling
     e2e = {"value": world * Be * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+           "copy_only_ceiling": world * Be * args.steps / (ms_copy / 1e3),
+           "copy_only_pcie_gbs_per_gpu": (4 * Be * no + 2 * Be * L) * N * 8 * args.steps / (ms_copy / 1e3) / 1e9,
            "h2d_bytes_per_step": 4 * Be * no * N * 8, "d2h_bytes_per_step": 2 * Be * L * N * 8,
            "batch": Be, "sub_batch": sb, "ms_per_step": ms_e2e / args.steps,
            "pcie_gbs": (4 * Be * no + 2 * Be * L) * N * 8 * args.steps / (ms_e2e / 1e3) / 1e9,
-           "note": "pinned host buffers; H2D / kernels / D2H pipelined over 3 streams (PCIe-bound)"}
+           "note": "pinned host buffers in the reference's int64 layout; H2D / kernels / D2H pipelined over 3 streams; "
+                   "copy_only_ceiling = the same copies with no kernels in between (what the host + PCIe side allows)"}
 
     ref_ext = None
     if rank == 0 and world == 1 and not args.no_reference_ext and not args.quick:
@@ -434,6 +441,11 @@ def run_ours(args):
 
     if rank == 0:
         alg_bytes = (6 * L + 4 + 2 * ng * E) * N * 8  # SURVEY.md 8(d), un-amortised
+        amort_bytes = (6 * L + 4 + 2 * ng * E / min(B, args.chunk)) * N * 8
+        measured_dram = None
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                measured_dram = json.load(f).get("hmult_dram_bytes_per_op")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -445,7 +457,13 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu, "reference_cuda_ext": ref_ext, "kernel_time_share": shares, "kernel_us_per_op": kernel_us_per_op,
             "hmult_hbm_roofline": {"algorithmic_bytes_per_op": alg_bytes, "roofline_ops_per_s": peak * 1e9 / alg_bytes,
-                                   "frac": value / world / (peak * 1e9 / alg_bytes)},
+                                   "frac": value / world / (peak * 1e9 / alg_bytes),
+                                   # keys shared by the ciphertexts of one chunk (what a batched call can amortise)
+                                   "amortised_bytes_per_op": amort_bytes,
+                                   "amortised_frac": value / world / (peak * 1e9 / amort_bytes),
+                                   # ncu dram__bytes_read + write summed over one chunk's launches / ciphertexts
+                                   "measured_dram_bytes_per_op": measured_dram,
+                                   "measured_dram_gbs": None if measured_dram is None else measured_dram * value / world / 1e9},
             "extra": extra, "limb_sharded": limb,
         }
         print(json.dumps(line), flush=True)

@@ -254,6 +254,22 @@ def check_ntt(s: Setup, level=0, with_special=True, batch=2):
     u = h.dev(wide)
     ctx.intt(u, pr[0], 2)
     eq(h, u, eng.intt(wide, pr, 2), "intt_radix2_exit_reduce on unreduced lazy input")
+    # products that land in the band where the Montgomery representative depends on floor(O S / 2^62): the first
+    # stage pairs j with j + N/2 under one twiddle S = w R, so O = r w^-1 mod q gives MM(S, O) = r (mod q) with
+    # r tiny -- half of them as the lazy value O + q (the deferred-reduction forward path, ExactSumPol, must
+    # follow the reference bit for bit through its integer fallback)
+    band = np.stack([s.rng.integers(0, 2 * int(o.q[g]), size=N, dtype=np.int64) for g in pr])
+    Rinv = [pow(1 << 62, -1, int(o.q[g])) for g in pr]
+    for r, g in enumerate(pr):
+        qg = int(o.q[g])
+        w = int(ctx.twiddles(False, g)[1]) * Rinv[r] % qg  # plain twiddle of stage 0
+        winv = pow(w, -1, qg)
+        small = s.rng.integers(0, 1 << 21, size=N // 2)
+        vals = [(int(v) * winv) % qg + (qg if (i & 1) else 0) for i, v in enumerate(small)]
+        band[r, N // 2:] = np.array(vals, dtype=np.int64)
+    u = h.dev(band)
+    ctx.ntt(u, pr[0], False)
+    eq(h, u, eng.ntt(band, pr), "ntt_radix2 with first-stage products on the representative boundary")
     # row-offset view (the reference's rescale outputs are views with storage offset N)
     big = h.dev(np.concatenate([a[0][:1], a[0]], axis=0))
     view = big[1:]

@@ -187,6 +187,53 @@ struct ExactF64Pol {
   }
 };
 
+// The same exact representatives at the cost of a mod-q butterfly, for tiles whose inputs all lie in [0, 2q)
+// (every value the reference's own operators hand to a forward transform).  With U in [0, 2q) and
+// V = MM(S, O) in [0, q + small], CS2(U + V) and CS2(U + 2q - V) ARE reductions modulo 2q, outputs stay in
+// [0, 2q), and V depends on O only through O mod q (outside the ~2^-20 band above).  So the lazy value after any
+// number of stages is T mod 2q, where T is the same butterfly network evaluated WITHOUT the conditional
+// subtractions: U' = U + V, O' = U - V, |T| < 2q + stages * (q + small) < 2^46 -- exact in a double.  The two
+// CS2 per butterfly (compare + predicated add each) and the two-sided canonicalisation disappear; what is
+// left is the error-free product, one sign fix and one band test: 11 FP64 instructions instead of 21.  The
+// kernels reduce T modulo 2q once per pass.
+__device__ __noinline__ double exact_sum_cold(double O, double q2, double inv2q, const u64* s4, u64 q4, u64 k) {
+  double y = __fma_rn(-FastF64Pol::round_int(__fma_rn(O, inv2q, TB_F64_MAGIC)), q2, O);  // O mod 2q, centred
+  y = y < 0.0 ? __dadd_rn(y, q2) : y;  // the reference's lazy value of this node
+  return FastF64Pol::from_int(tb_mm_s4(FastF64Pol::to_int(y), __ldg(s4), q4, k));
+}
+struct ExactSumPol {
+  FastF64Pol f;
+  PrimeRegs p;
+  double q2, inv2q, xbmax;  // 2q, 1/(2q), band below which MM's representative depends on floor(O S / 2^62)
+  const double* twd;
+  const u64* psi4;
+  typedef ExactF64Pol::TW TW;
+  typedef double TWS;
+  __device__ __forceinline__ TW load(const TWS* t) const {
+    TW r;
+    r.w = __ldg(t);
+    r.s4 = psi4 + (t - twd);
+    return r;
+  }
+  __device__ __forceinline__ void ct(i64& Ub, i64& Ob, TW S, int) const {
+    const double U = __longlong_as_double(Ub), O = __longlong_as_double(Ob);
+    double V = f.mulmod(O, S.w);  // centred residue of O S 2^-62
+    if ((V < 0.0 ? -V : V) < xbmax)
+      V = exact_sum_cold(O, q2, inv2q, S.s4, p.q4, p.k);
+    else
+      V = V < 0.0 ? __dadd_rn(V, f.q) : V;
+    Ub = __double_as_longlong(__dadd_rn(U, V));
+    Ob = __double_as_longlong(__dadd_rn(U, -V));
+  }
+  // T -> T mod 2q in [0, 2q), as an integer
+  __device__ __forceinline__ i64 finish(i64 Tb) const {
+    const double T = __longlong_as_double(Tb);
+    double y = __fma_rn(-FastF64Pol::round_int(__fma_rn(T, inv2q, TB_F64_MAGIC)), q2, T);
+    y = y < 0.0 ? __dadd_rn(y, q2) : y;
+    return FastF64Pol::to_int(y);
+  }
+};
+
 // any q < 2^60: Harvey lazy butterflies, forward values in [0, 4q), inverse values in [0, 2q).
 struct FastBigPol {
   u64 q, q2;

@@ -182,6 +182,25 @@ __device__ __forceinline__ bool tile_fits_f64(const TbDev& c, int g, const i64 (
   for (int i = 0; i < 16; ++i) bad |= (x[i] >= (1ll << 50)) | (x[i] <= -(1ll << 50));
   return !tb_block_any(bad);  // barrier + OR over the CTA (no shared flag written by several threads)
 }
+// CTA-uniform: every residue of the tile in [0, hi)?  (hi = 2q: the lazy range the ExactSumPol shortcut needs)
+__device__ __forceinline__ bool tile_in_range(const i64 (&x)[16], i64 hi) {
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) bad |= (x[i] < 0) | (x[i] >= hi);
+  return !tb_block_any(bad);
+}
+__device__ __forceinline__ tb::ExactSumPol exact_sum_policy(const TbDev& c, int g, const tb::PrimeRegs& p, const u64* psi4) {
+  const TbFastPrime& F = c.fp[g];
+  tb::ExactSumPol pol;
+  pol.f = tb::FastF64Pol{F.qd, F.qinv};
+  pol.p = p;
+  pol.q2 = F.qd + F.qd;
+  pol.inv2q = 0.5 * F.qinv;
+  pol.xbmax = pol.q2 * F.qd * 2.168404344971008868e-19 + 4.0;  // |O| < 2q: floor(O S / 2^62) < 2q q 2^-62 + 1
+  pol.twd = c.twd + ((long)g << c.logN);
+  pol.psi4 = psi4 + ((long)g << c.logN);
+  return pol;
+}
 __device__ __forceinline__ tb::ExactF64Pol exact_f64_policy(const TbDev& c, int g, const tb::PrimeRegs& p, const u64* psi4) {
   const TbFastPrime& F = c.fp[g];
   tb::ExactF64Pol pol;
@@ -212,6 +231,9 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbVie
     const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
     const i64 Rs = c.pr[g].Rs;
     const double Rc = c.fp[g].Rcd;  // R mod q, centred
+    // non-negative inputs (enter: below 2^50, MM(x, R^2) then lies in [0, q + small]; plain: lazy values below
+    // 2q): the conditional subtractions can be deferred to one reduction modulo 2q (ExactSumPol)
+    const bool sum = tile_in_range(x, PRO == TB_PRO_ENTER ? (1ll << 50) : p.q2);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       double v = tb::FastF64Pol::from_int(x[i]);
@@ -224,6 +246,13 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbVie
         v = r;
       }
       x[i] = __double_as_longlong(v);
+    }
+    if (sum) {
+      const tb::ExactSumPol sp = exact_sum_policy(c, g, p, c.psi4);
+      tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, sp.twd, sp, slot);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = sp.finish(x[i]);
+      return;
     }
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, pol.twd, pol, slot);
 #pragma unroll
@@ -261,12 +290,20 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_B(TbDev c, TbView src, TbVie
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
   if (tile_fits_f64(c, g, x)) {
-    const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
+    const bool sum = tile_in_range(x, p.q2);
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(tb::FastF64Pol::from_int(x[i]));
-    tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, pol.twd, pol, slot);
+    if (sum) {
+      const tb::ExactSumPol sp = exact_sum_policy(c, g, p, c.psi4);
+      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, sp.twd, sp, slot);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = tb::FastF64Pol::to_int(__longlong_as_double(x[i]));
+      for (int i = 0; i < 16; ++i) x[i] = sp.finish(x[i]);
+    } else {
+      const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
+      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, pol.twd, pol, slot);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = tb::FastF64Pol::to_int(__longlong_as_double(x[i]));
+    }
   } else {
     tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   }
