@@ -570,6 +570,9 @@ extern "C" int tb200_ctx_set_tuning(tb200_ctx* c, int knob, int value) {
     case TB200_TUNE_STREAM_WS:
       c->stream_ws = value != 0;
       return 0;
+    case TB200_TUNE_SUM_NTT:
+      c->sum_ntt = value != 0;
+      return 0;
   }
   return fail(TB200_EINVAL, "unknown tuning knob %d", knob);
 }
@@ -739,15 +742,22 @@ static inline int ntt_lw(const tb200_ctx* c) {  // log2 of the column width of a
   return lw;
 }
 
+// flags != nullptr: the deferred-reduction kernel first (it flags the tiles it leaves), then the generic kernel on
+// the flagged tiles only
 template <int PRO>
-static int launch_fwd_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, tb200_stream st) {
+static int launch_fwd_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, tb200_stream st,
+                        unsigned char* flags = nullptr) {
   const int lw = ntt_lw(c);
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
   switch (c->LA) {
 #define ACASE(n)                                            \
   case n: {                                                 \
+    if (flags) {                                            \
+      auto ksum = k_ntt_fwd_A_sum<n, PRO>;                  \
+      LAUNCHN("k_ntt_fwd_A_sum", ksum, grid, block, st, c->dev(), src, dst, prime0, lw, flags); \
+    }                                                       \
     auto kfn = k_ntt_fwd_A<n, PRO>;                         \
-    LAUNCHN("k_ntt_fwd_A", kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
+    LAUNCHN("k_ntt_fwd_A", kfn, grid, block, st, c->dev(), src, dst, prime0, lw, (const unsigned char*)flags); \
   } break;
     ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
 #undef ACASE
@@ -774,7 +784,7 @@ static int launch_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, in
   return 0;
 }
 static int launch_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, int rows, int batch, int prime0,
-                    tb200_stream st) {
+                    tb200_stream st, unsigned char* flags = nullptr) {
   const int te = c->N < TB_TILE ? c->N : TB_TILE;
   const dim3 grid((unsigned)(c->N / te), (unsigned)rows, (unsigned)batch), block((unsigned)(te / 16));
   switch (c->LB) {
@@ -784,8 +794,12 @@ static int launch_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, in
       auto kfn = k_ntt_inv_B<n>;                                 \
       LAUNCHN("k_ntt_inv_B", kfn, grid, block, st, c->dev(), src, dst, prime0);  \
     } else {                                                     \
+      if (flags) {                                               \
+        auto ksum = k_ntt_fwd_B_sum<n>;                          \
+        LAUNCHN("k_ntt_fwd_B_sum", ksum, grid, block, st, c->dev(), src, dst, prime0, flags); \
+      }                                                          \
       auto kfn = k_ntt_fwd_B<n>;                                 \
-      LAUNCHN("k_ntt_fwd_B", kfn, grid, block, st, c->dev(), src, dst, prime0);  \
+      LAUNCHN("k_ntt_fwd_B", kfn, grid, block, st, c->dev(), src, dst, prime0, (const unsigned char*)flags);  \
     }                                                            \
   } break;
     BCASE(4) BCASE(5) BCASE(6) BCASE(7) BCASE(8)
@@ -796,12 +810,18 @@ static int launch_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, in
   return 0;
 }
 
+// number of CTA tiles of one pass (= bytes of one flag array)
+static size_t ntt_tiles(const tb200_ctx* c, int rows, int batch) {
+  const int te = c->N < TB_TILE ? c->N : TB_TILE;
+  return (size_t)(c->N / te) * rows * batch;
+}
+// flags: 2 * ntt_tiles zeroed bytes (one array per pass) or nullptr (generic kernels only)
 static int ntt_forward(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, bool enter,
-                       tb200_stream st) {
-  int rc = enter ? launch_fwd_A<TB_PRO_ENTER>(c, src, dst, rows, batch, prime0, st)
-                 : launch_fwd_A<TB_PRO_NONE>(c, src, dst, rows, batch, prime0, st);
+                       tb200_stream st, unsigned char* flags = nullptr) {
+  int rc = enter ? launch_fwd_A<TB_PRO_ENTER>(c, src, dst, rows, batch, prime0, st, flags)
+                 : launch_fwd_A<TB_PRO_NONE>(c, src, dst, rows, batch, prime0, st, flags);
   if (rc) return rc;
-  return launch_B(c, false, dst, dst, rows, batch, prime0, st);
+  return launch_B(c, false, dst, dst, rows, batch, prime0, st, flags ? flags + ntt_tiles(c, rows, batch) : nullptr);
 }
 static int ntt_inverse(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, int mode,
                        tb200_stream st) {
@@ -827,7 +847,17 @@ extern "C" int tb200_ntt(tb200_ctx* c, int rows, int batch, int prime0, const tb
   CHECK_POLY(a);
   if (batch < 1) return fail(TB200_EINVAL, "batch must be >= 1");
   SET_DEVICE(c->device);
-  int rc = ntt_forward(c, view(a), view(a), rows, batch, prime0, enter != 0, st);
+  // 40-bit limbs with lazy inputs take the deferred-reduction kernels (same bits, tb200_fast.cuh: ExactSumPol)
+  WsLease ws(c, st);
+  unsigned char* flags = nullptr;
+  int rc = 0;
+  if (c->fast && c->sum_ntt) {
+    const size_t nbytes = 2 * ntt_tiles(c, rows, batch);
+    if ((rc = ws.reserve((nbytes + 7) / 8))) return rc;
+    flags = reinterpret_cast<unsigned char*>(ws.p);
+    CK(cudaMemsetAsync(flags, 0, nbytes, (cudaStream_t)st));
+  }
+  rc = ntt_forward(c, view(a), view(a), rows, batch, prime0, enter != 0, st, flags);
   if (rc) return rc;
   POST();
   return 0;

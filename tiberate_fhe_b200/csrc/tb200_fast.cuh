@@ -196,32 +196,23 @@ struct ExactF64Pol {
 // CS2 per butterfly (compare + predicated add each) and the two-sided canonicalisation disappear; what is
 // left is the error-free product, one sign fix and one band test: 11 FP64 instructions instead of 21.  The
 // kernels reduce T modulo 2q once per pass.
-__device__ __noinline__ double exact_sum_cold(double O, double q2, double inv2q, const u64* s4, u64 q4, u64 k) {
-  double y = __fma_rn(-FastF64Pol::round_int(__fma_rn(O, inv2q, TB_F64_MAGIC)), q2, O);  // O mod 2q, centred
-  y = y < 0.0 ? __dadd_rn(y, q2) : y;  // the reference's lazy value of this node
-  return FastF64Pol::from_int(tb_mm_s4(FastF64Pol::to_int(y), __ldg(s4), q4, k));
-}
+// The band cases are not resolved inside the butterfly: the policy only records the smallest |V| it met, and a
+// tile that saw one inside the band (about 3 % of the 4096-point tiles at logN16) is transformed again with
+// ExactF64Pol from its untouched input.  The hot loop is then branch-free.
 struct ExactSumPol {
   FastF64Pol f;
-  PrimeRegs p;
   double q2, inv2q, xbmax;  // 2q, 1/(2q), band below which MM's representative depends on floor(O S / 2^62)
-  const double* twd;
-  const u64* psi4;
-  typedef ExactF64Pol::TW TW;
+  unsigned* minhi;          // smallest high word of |V| seen by this thread (non-negative doubles order like
+                            // their bit patterns: two integer instructions instead of an FP64 min)
+  typedef double TW;
   typedef double TWS;
-  __device__ __forceinline__ TW load(const TWS* t) const {
-    TW r;
-    r.w = __ldg(t);
-    r.s4 = psi4 + (t - twd);
-    return r;
-  }
-  __device__ __forceinline__ void ct(i64& Ub, i64& Ob, TW S, int) const {
+  static __device__ __forceinline__ TW load(const TWS* t) { return __ldg(t); }
+  __device__ __forceinline__ void ct(i64& Ub, i64& Ob, TW w, int) const {
     const double U = __longlong_as_double(Ub), O = __longlong_as_double(Ob);
-    double V = f.mulmod(O, S.w);  // centred residue of O S 2^-62
-    if ((V < 0.0 ? -V : V) < xbmax)
-      V = exact_sum_cold(O, q2, inv2q, S.s4, p.q4, p.k);
-    else
-      V = V < 0.0 ? __dadd_rn(V, f.q) : V;
+    double V = f.mulmod(O, w);  // centred residue of O S 2^-62
+    const unsigned hi = (unsigned)((u64)__double_as_longlong(V) >> 32);
+    *minhi = min(*minhi, hi & 0x7fffffffu);
+    V = (hi >> 31) ? __dadd_rn(V, f.q) : V;  // sign bit from the integer side
     Ub = __double_as_longlong(__dadd_rn(U, V));
     Ob = __double_as_longlong(__dadd_rn(U, -V));
   }

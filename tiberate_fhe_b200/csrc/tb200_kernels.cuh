@@ -189,16 +189,14 @@ __device__ __forceinline__ bool tile_in_range(const i64 (&x)[16], i64 hi) {
   for (int i = 0; i < 16; ++i) bad |= (x[i] < 0) | (x[i] >= hi);
   return !tb_block_any(bad);
 }
-__device__ __forceinline__ tb::ExactSumPol exact_sum_policy(const TbDev& c, int g, const tb::PrimeRegs& p, const u64* psi4) {
+__device__ __forceinline__ tb::ExactSumPol exact_sum_policy(const TbDev& c, int g, unsigned* minhi) {
   const TbFastPrime& F = c.fp[g];
   tb::ExactSumPol pol;
   pol.f = tb::FastF64Pol{F.qd, F.qinv};
-  pol.p = p;
   pol.q2 = F.qd + F.qd;
   pol.inv2q = 0.5 * F.qinv;
   pol.xbmax = pol.q2 * F.qd * 2.168404344971008868e-19 + 4.0;  // |O| < 2q: floor(O S / 2^62) < 2q q 2^-62 + 1
-  pol.twd = c.twd + ((long)g << c.logN);
-  pol.psi4 = psi4 + ((long)g << c.logN);
+  pol.minhi = minhi;
   return pol;
 }
 __device__ __forceinline__ tb::ExactF64Pol exact_f64_policy(const TbDev& c, int g, const tb::PrimeRegs& p, const u64* psi4) {
@@ -213,9 +211,17 @@ __device__ __forceinline__ tb::ExactF64Pol exact_f64_policy(const TbDev& c, int 
   return pol;
 }
 
+// CTA index into the "left for the generic kernel" flag array of the deferred-reduction kernels below
+__device__ __forceinline__ long tile_flag_index() {
+  return ((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+}
+
+// todo != nullptr: second launch after k_ntt_fwd_A_sum -- only the tiles that kernel flagged are transformed
 template <int LA, int PRO>
-__global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbView dst, int prime0, int LW) {
+__global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbView dst, int prime0, int LW,
+                                                      const unsigned char* todo) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  if (todo != nullptr && todo[tile_flag_index()] == 0) return;
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -231,9 +237,6 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbVie
     const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
     const i64 Rs = c.pr[g].Rs;
     const double Rc = c.fp[g].Rcd;  // R mod q, centred
-    // non-negative inputs (enter: below 2^50, MM(x, R^2) then lies in [0, q + small]; plain: lazy values below
-    // 2q): the conditional subtractions can be deferred to one reduction modulo 2q (ExactSumPol)
-    const bool sum = tile_in_range(x, PRO == TB_PRO_ENTER ? (1ll << 50) : p.q2);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       double v = tb::FastF64Pol::from_int(x[i]);
@@ -246,13 +249,6 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbVie
         v = r;
       }
       x[i] = __double_as_longlong(v);
-    }
-    if (sum) {
-      const tb::ExactSumPol sp = exact_sum_policy(c, g, p, c.psi4);
-      tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, sp.twd, sp, slot);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = sp.finish(x[i]);
-      return;
     }
     tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, pol.twd, pol, slot);
 #pragma unroll
@@ -271,8 +267,10 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_A(TbDev c, TbView src, TbVie
 
 // forward pass B: stages LA..logN-1 on contiguous 2^LB blocks; a CTA owns TE = blockDim*16 residues.
 template <int LB>
-__global__ void __launch_bounds__(256, 3) k_ntt_fwd_B(TbDev c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256, 3) k_ntt_fwd_B(TbDev c, TbView src, TbView dst, int prime0,
+                                                      const unsigned char* todo) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  if (todo != nullptr && todo[tile_flag_index()] == 0) return;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
   const tb::PrimeRegs p = load_prime(c.pr, g);
@@ -290,20 +288,12 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_B(TbDev c, TbView src, TbVie
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = sm[slot(tb::tile_x(lt, i, f0))];
   if (tile_fits_f64(c, g, x)) {
-    const bool sum = tile_in_range(x, p.q2);
+    const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(tb::FastF64Pol::from_int(x[i]));
-    if (sum) {
-      const tb::ExactSumPol sp = exact_sum_policy(c, g, p, c.psi4);
-      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, sp.twd, sp, slot);
+    tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, pol.twd, pol, slot);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = sp.finish(x[i]);
-    } else {
-      const tb::ExactF64Pol pol = exact_f64_policy(c, g, p, c.psi4);
-      tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, pol.twd, pol, slot);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = tb::FastF64Pol::to_int(__longlong_as_double(x[i]));
-    }
+    for (int i = 0; i < 16; ++i) x[i] = tb::FastF64Pol::to_int(__longlong_as_double(x[i]));
   } else {
     tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.psi4 + ((long)g << c.logN), tb::ExactPol{p}, slot);
   }
@@ -313,6 +303,114 @@ __global__ void __launch_bounds__(256, 3) k_ntt_fwd_B(TbDev c, TbView src, TbVie
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[i * nt + tid] = sm[tb::pad16(i * nt + tid)];
+}
+
+// ---- deferred-reduction forward transforms (ExactSumPol) ---------------------------------------------------
+// Same grids as k_ntt_fwd_A / k_ntt_fwd_B.  A tile is transformed here iff its prime takes the FP64 route, every
+// input lies in the lazy range and no product fell into the representative band; otherwise the CTA leaves the
+// tile untouched and sets todo[tile], and the generic kernel (launched right after with the same flag array)
+// transforms it.  Without the integer and per-butterfly-test code paths these kernels fit 64 registers.
+template <int LA, int PRO>
+__global__ void __launch_bounds__(256, 4) k_ntt_fwd_A_sum(TbDev c, TbView src, TbView dst, int prime0, int LW,
+                                                          unsigned char* todo) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int W = 1 << LW;
+  const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime& F = c.fp[g];
+  if (!c.x64 || !F.f64) {
+    if (threadIdx.x == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+  const i64* s = src.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  i64* d = dst.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  constexpr int f0 = tb::fwd_field<LA>(0);
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = s[(long)tb::tile_x(tr, i, f0) << c.LB];
+  unsigned minhi = 0x7fffffffu;
+  const tb::ExactSumPol sp = exact_sum_policy(c, g, &minhi);
+  // |V| < xbmax is implied by hiword(|V|) <= hiword(xbmax): test the (slightly wider) word-granular band
+  const unsigned band_hi = (unsigned)((u64)__double_as_longlong(sp.xbmax) >> 32) + 1u;
+  // enter: non-negative inputs below 2^50 -- MM(x, R^2) then lies in [0, q + small] and equals the canonical
+  // residue outside the band (tested on |r| like the butterflies); plain: lazy values in [0, 2q)
+  bool bad = false;
+  const i64 hi = PRO == TB_PRO_ENTER ? (1ll << 50) : (i64)(2 * F.q);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bad |= (x[i] < 0) | (x[i] >= hi);
+    double v = tb::FastF64Pol::from_int(x[i]);
+    if constexpr (PRO == TB_PRO_ENTER) {
+      double r = sp.f.mulmod(v, F.Rcd);
+      const double xb = __fma_rn(v, sp.f.q * 2.168404344971008868e-19, 2.0);  // floor(x R^2 / 2^62) <= x q 2^-62 + 1
+      bad |= (r < 0.0 ? -r : r) < xb;
+      v = r < 0.0 ? __dadd_rn(r, sp.f.q) : r;
+    }
+    x[i] = __double_as_longlong(v);
+  }
+  auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
+  tb::tile_fwd<LA>(x, sm, tr, 0, LA - 1, c.twd + ((long)g << c.logN), sp, slot);
+  if (tb_block_any(bad | (minhi < band_hi))) {
+    if (threadIdx.x == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, 0) << c.LB] = sp.finish(x[i]);
+}
+
+template <int LB>
+__global__ void __launch_bounds__(256, 4) k_ntt_fwd_B_sum(TbDev c, TbView src, TbView dst, int prime0,
+                                                          unsigned char* todo) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime& F = c.fp[g];
+  if (!c.x64 || !F.f64) {
+    if (tid == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+  const long e0 = (long)blockIdx.x * nt * 16;
+  const i64* s = src.row(blockIdx.z, limb) + e0;
+  i64* d = dst.row(blockIdx.z, limb) + e0;
+  const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
+  const int tile = (int)(e0 >> LB) + blk;
+  auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
+  constexpr int f0 = tb::fwd_field<LB>(0);
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
+  unsigned minhi = 0x7fffffffu;
+  const tb::ExactSumPol sp = exact_sum_policy(c, g, &minhi);
+  // |V| < xbmax is implied by hiword(|V|) <= hiword(xbmax): test the (slightly wider) word-granular band
+  const unsigned band_hi = (unsigned)((u64)__double_as_longlong(sp.xbmax) >> 32) + 1u;
+  bool bad = false;
+  const i64 hi = (i64)(2 * F.q);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bad |= (x[i] < 0) | (x[i] >= hi);
+    x[i] = __double_as_longlong(tb::FastF64Pol::from_int(x[i]));
+  }
+  tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.twd + ((long)g << c.logN), sp, slot);
+  if (tb_block_any(bad | (minhi < band_hi))) {
+    if (tid == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = sp.finish(x[i]);
+  // field-0 layout -> coalesced 128-bit stores through shared memory (as k_fast_fwd_B)
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
+  __syncthreads();
+  longlong2* dv = reinterpret_cast<longlong2*>(d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = 2 * (i * nt + tid);
+    longlong2 v;
+    v.x = sm[tb::pad16(e)];
+    v.y = sm[tb::pad16(e + 1)];
+    dv[i * nt + tid] = v;
+  }
 }
 
 // inverse pass B': inverse stages 0..LB-1 (distances 1..2^(LB-1)) on contiguous blocks.
