@@ -220,6 +220,16 @@ int tb200_relinearize(tb200_ctx*, int level, int batch, const tb200_poly* d0, co
  * polynomials, then switch_key with rotk.  With ksk == NULL only the automorphism is applied. */
 int tb200_rotate(tb200_ctx*, int level, int batch, int64_t galois, const tb200_poly* c0, const tb200_poly* c1,
                  const tb200_ksk* rotk, const tb200_poly* out0, const tb200_poly* out1, tb200_stream);
+/* Hoisted rotations (extension; the reference rotates one key at a time): `nrot` rotations of the same
+ * ciphertext(s) share the ModUp digits, the extension and its forward transform; per rotation only the key inner
+ * product (reading the extension through the NTT-domain automorphism), the inverse transform and ModDown remain.
+ * galois[r] / rotks[r]: Galois element and rotation key of rotation r; rotation r is written at
+ * out0->ptr + r * rot_stride (same batch / row strides for every rotation).  The results decrypt like
+ * tb200_rotate's but are not bit-identical to them (the digits are taken before the automorphism);
+ * oracle/engine.py: rotate_hoisted is the bit-exact restatement. */
+int tb200_rotate_hoisted(tb200_ctx*, int level, int batch, int nrot, const int64_t* galois, const tb200_poly* c0,
+                         const tb200_poly* c1, const tb200_ksk* const* rotks, const tb200_poly* out0,
+                         const tb200_poly* out1, int64_t rot_stride, tb200_stream);
 /* switch_key :1403-1420 (ct.c0 + ks0, ks1). */
 int tb200_switch_key(tb200_ctx*, int level, int batch, const tb200_poly* c0, const tb200_poly* c1,
                      const tb200_ksk* ksk, const tb200_poly* out0, const tb200_poly* out1, tb200_stream);

@@ -212,6 +212,49 @@ class OracleEngine:
         rot = [self.codec_rotate(_c(ct[0]), level, perm), self.codec_rotate(_c(ct[1]), level, perm)]
         return self.switch_key(rot, rotk, level)
 
+    def ntt_slot_perm(self, galois):
+        """X -> X^g in the NTT domain: slot i holds the evaluation at psi^(2 brev(i) + 1), and
+        (sigma_g a)(psi^e) = a(psi^(e g)), so slot i of sigma_g(a) is slot brev(((2 brev(i)+1) g mod 2N - 1)/2) of a."""
+        from .context import bit_reverse
+
+        N, logN = self.ctx.N, self.ctx.logN
+        br = np.array([bit_reverse(i, logN) for i in range(N)], dtype=np.int64)
+        e = ((2 * br + 1) * int(galois)) % (2 * N)
+        return br[(e - 1) // 2]  # brev is an involution: br[x] = brev(x)
+
+    def rotate_hoisted(self, ct, rotks, deltas, level):
+        """Hoisted rotations (an extension beyond the reference; restates tb200_rotate_hoisted): the digits,
+        extension and forward transform of c1 are computed ONCE (as in create_switcher, ckks_engine.py:1201-1400),
+        each rotation applies the automorphism to the transformed extension (a slot permutation), multiplies by its
+        own key, and finishes as switch_key does (:1316-1363, :1403-1420) with the rotated c0."""
+        ctx = self.ctx
+        tgt = ctx.level_primes(level, True)
+        order = {g: pr for g, pr in ctx.part.level_groups(level)}
+        exts = []
+        for g in ctx.part.storage_order(level):
+            state = self.pre_extend(_c(ct[1]), level, order[g])
+            exts.append((g, self.ntt(self.extend(state, level, order[g]), tgt)))
+        q, _ = ctx.rows(tgt)
+        qo, _ = ctx.rows(ctx.level_primes(level, False))
+        outs = []
+        for delta in deltas:
+            d = delta % ctx.N
+            gal = (2 * ((3 ** d - 1) // 2 % (2 * ctx.N)) + 1) % (2 * ctx.N)
+            pi = self.ntt_slot_perm(gal)
+            ksk = rotks[delta]
+            halves = []
+            for which in (0, 1):
+                parts = [self.mont_mult(_c(ext[:, pi]), _c(ksk[g][which][level:]), tgt) for g, ext in exts]
+                st = _c(np.stack(parts))
+                acc = np.empty_like(st[0])
+                call("orc_mont_reduce_add_many_3d", acc, st, st.shape[0], st.shape[1], st.shape[2], q)
+                halves.append(self.divide_by_p(self.intt(acc, tgt, 2), level))
+            r0 = self.codec_rotate(_c(ct[0]), level, self.galois_perm(delta))
+            new0 = np.empty_like(r0)
+            call("orc_mont_add_reduce_2q", new0, r0, halves[0], r0.shape[0], r0.shape[1], qo)
+            outs.append([new0, halves[1]])
+        return outs
+
     # ------------------------------------------------------------------ add / plaintext mult
     def cc_add(self, a, b, level):
         """ckks_engine.py:1932-1956."""

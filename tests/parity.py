@@ -333,13 +333,14 @@ ENGINE_MODES = ((False, 0), (True, 0), (True, 3), (True, 8, 0, 1), (True, 8))  #
 
 def set_mode(s: "Setup", mode):
     fast, share = mode[0], mode[1]
+    s.fast_mode = bool(fast)
     s.ctx.set_fast(fast)
     s.ctx.set_f64_share(share)
     s.ctx.set_tuning(s.ctx.TUNE_FUSED_CORE, mode[2] if len(mode) > 2 else 1)
     s.ctx.set_tuning(s.ctx.TUNE_FUSED_MODDOWN, mode[3] if len(mode) > 3 else 0)
 
 
-def check_engine(s: Setup, level: int, batch=None, ops=("rescale", "keyswitch", "switch_key", "rotate", "cc_mult",
+def check_engine(s: Setup, level: int, batch=None, ops=("rescale", "keyswitch", "switch_key", "rotate", "hoisted", "cc_mult",
                                                         "triplet", "pc_mult", "addsub")):
     h, o, eng, ctx = s.h, s.octx, s.eng, s.ctx
     N = s.N
@@ -388,6 +389,19 @@ def check_engine(s: Setup, level: int, batch=None, ops=("rescale", "keyswitch", 
             perm = eng.galois_perm(delta)
             w = each(lambda a, b: [eng.codec_rotate(a[0], level, perm), eng.codec_rotate(a[1], level, perm)])
             eq(h, o0, w[0], f"automorphism only delta {delta} c0")
+    if "hoisted" in ops and s.rotk and getattr(s, "fast_mode", True):  # hoisting exists on the mod-q path only
+        deltas = list(s.rotk)
+        R = len(deltas)
+        o0, o1 = h.zeros(R, *shp), h.zeros(R, *shp)
+        ctx.rotate_hoisted(level, [galois_element(N, d) for d in deltas], d1[0], d1[1], [s.rotk_d[d] for d in deltas], o0, o1)
+        g0, g1 = h.host(o0), h.host(o1)
+        for b in range(B):
+            one = [ct1[0], ct1[1]] if batch is None else [ct1[0][b], ct1[1][b]]
+            want = eng.rotate_hoisted(one, s.rotk, deltas, level)
+            for r, d in enumerate(deltas):
+                got = (g0[r], g1[r]) if batch is None else (g0[r][b], g1[r][b])
+                assert np.array_equal(got[0], want[r][0]), f"rotate_hoisted delta {d} level {level} c0 (batch entry {b})"
+                assert np.array_equal(got[1], want[r][1]), f"rotate_hoisted delta {d} level {level} c1 (batch entry {b})"
     if "cc_mult" in ops:
         for pre in ((True, False) if can_rescale else (False,)):
             sh = shp1 if pre else shp

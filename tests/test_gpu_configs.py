@@ -180,10 +180,24 @@ def test_config5_matvec_logN14_oracle_composition_and_decrypt():
     assert acc.level == lvl1
     assert np.array_equal(acc.data[0][0].cpu().numpy(), oacc[0]), "mat-vec c0 differs from the oracle composition"
     assert np.array_equal(acc.data[1][0].cpu().numpy(), oacc[1]), "mat-vec c1 differs from the oracle composition"
+    # 1b. the same product with hoisted rotations (rot_i of the input, key rotk[i], one ModUp for all): every rotation
+    # equals the oracle's restatement of the hoisted algorithm bit for bit, and the sum decrypts to the same product
+    hoisted = eng.rotate_hoisted(ct, range(1, D))
+    ohoist = orc.rotate_hoisted([ct.data[0][0].cpu().numpy(), ct.data[1][0].cpu().numpy()],
+                                {d: _ksk_numpy(eng.rotk[d]) for d in range(1, D)}, list(range(1, D)), level)
+    for r, (got, want) in enumerate(zip(hoisted, ohoist)):
+        assert np.array_equal(got.data[0][0].cpu().numpy(), want[0]), f"hoisted rotation {r + 1} c0"
+        assert np.array_equal(got.data[1][0].cpu().numpy(), want[1]), f"hoisted rotation {r + 1} c1"
+    acc_h = eng.pc_mult(pts[0], ct)
+    for i in range(1, D):
+        acc_h = eng.cc_add(acc_h, eng.pc_mult(pts[i], hoisted[i - 1]))
+    dec_h = torch.as_tensor(np.asarray(eng.decryptcode(acc_h, is_real=True)), dtype=torch.float64)[:n]
     # 2. decrypts to the plaintext product (either rotation direction convention, fixed over the sum)
     dec = torch.as_tensor(np.asarray(eng.decryptcode(acc, is_real=True)), dtype=torch.float64)[:n]
     errs = []
     for sgn in (-1, 1):
         want = sum(diags[i] * torch.roll(v, sgn * i) for i in range(D))
         errs.append((dec - want).abs().max().item())
-    assert min(errs) < 1e-4 * max(1.0, float(sum(d.abs().max() for d in diags) * v.abs().max())), errs
+    tol = 1e-4 * max(1.0, float(sum(d.abs().max() for d in diags) * v.abs().max()))
+    assert min(errs) < tol, errs
+    assert (dec_h - dec).abs().max().item() < tol, "hoisted mat-vec decrypts to something else than the chained one"

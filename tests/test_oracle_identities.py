@@ -122,3 +122,28 @@ def test_partition_matches_survey_table():
     p2 = Partition(17, 2, num_devices=2)  # rns_partition.py defaults
     assert p2.part_allocations[0][-2:] == [8, 9] and p2.part_allocations[1][-1] == 9
     assert sorted(p2.part_allocations[0][:-2] + p2.part_allocations[1][:-1]) == list(range(8))
+
+
+def test_hoisted_rotations_decrypt_to_the_rotated_message():
+    """rotate_hoisted (an extension beyond the reference, restated in oracle/engine.py) shares the ModUp between
+    rotations; its outputs need not equal rotate_single's bits but must decrypt to the same rotated message."""
+    logN = 6
+    ctx = OracleContext(logN, toy_primes(logN, 7, 3), 3)
+    eng = OracleEngine(ctx)
+    N = ctx.N
+    rng = np.random.default_rng(5)
+    sk, _ = eng.gen_secret(rng)
+    pk = eng.gen_public(rng, sk, True)
+    scale = 1 << 40
+    m = rng.integers(-50, 50, size=N)
+    deltas = [1, 3, 7]
+    rotks = {d: eng.gen_rotk(rng, sk, d) for d in deltas}
+    for level in (0, 2):
+        ct = eng.encrypt_poly(rng, m * scale, pk, level)
+        outs = eng.rotate_hoisted(ct, rotks, deltas, level)
+        for d, out in zip(deltas, outs):
+            want = eng.rotate_plain((m * scale)[None, :], d)[0]
+            got = eng.decrypt_poly(out, sk, level)
+            assert max(abs(x - int(e)) for x, e in zip(got, want)) < 2000, (level, d)
+            single = eng.decrypt_poly(eng.rotate_single(ct, rotks[d], d, level), sk, level)
+            assert max(abs(x - y) for x, y in zip(got, single)) < 4000

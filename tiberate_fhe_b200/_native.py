@@ -73,6 +73,7 @@ SIGNATURES = {
     "tb200_cc_mult_triplet": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_relinearize": (_i, [_vp, _i, _i, PP, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),
     "tb200_rotate": (_i, [_vp, _i, _i, _i64, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),
+    "tb200_rotate_hoisted": (_i, [_vp, _i, _i, _i, _vp, PP, PP, _vp, PP, PP, C.c_int64, _vp]),
     "tb200_switch_key": (_i, [_vp, _i, _i, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),
     "tb200_pc_mult": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_addsub": (_i, [_vp, _i, _i, _i, PP, PP, PP, PP, PP, PP, _vp]),

@@ -66,7 +66,6 @@ class CkksEngine(KeyGenMixin, CodecMixin, LevelMixin):
         wrapper.set_context(self.ctx)
         self.logN, self.N = self.ctx.logN, self.ctx.N
         self.num_special_primes = self.ctx.K
-        self._keys = {}
         self._init_keygen(seed, nonce)  # CSPRNG + key-generation constants (keygen.py)
         self._init_codec(bias_guard, norm)
 
@@ -81,17 +80,17 @@ class CkksEngine(KeyGenMixin, CodecMixin, LevelMixin):
     # ---- helpers -------------------------------------------------------------------------------
     def _key(self, ksk: KeySwitchKey) -> KeySwitchKeyView:
         """KeySwitchKey.data = list over global digit-group id of PublicKey(data=[[b],[a]])."""
-        v = self._keys.get(id(ksk))
-        if v is None or v[0] is not ksk:
+        v = getattr(ksk, "_tb200_view", None)  # cached on the key object: lives and dies with it
+        if v is None:
             parts = []
             for part in ksk.data:
                 if part is None or (isinstance(part, list) and len(part) == 0):
                     parts.append(None)
                 else:
                     parts.append((part.data[0][0], part.data[1][0]))
-            v = (ksk, KeySwitchKeyView(parts, self.N))
-            self._keys[id(ksk)] = v
-        return v[1]
+            v = KeySwitchKeyView(parts, self.N)
+            ksk._tb200_view = v
+        return v
 
     @staticmethod
     def _t(poly_list):
@@ -177,6 +176,21 @@ class CkksEngine(KeyGenMixin, CodecMixin, LevelMixin):
         o0, o1 = torch.empty_like(c0), torch.empty_like(c1)
         self.ctx.rotate(ct.level, g, c0, c1, self._key(rotk) if post_key_switching else None, o0, o1)
         return Ciphertext(data=[[o0], [o1]], flags=ct._flags, level=ct.level, misc=dict(ct.misc))
+
+    def rotate_hoisted(self, ct: Ciphertext, deltas, rotks=None):
+        """Rotations of ONE ciphertext by every delta in `deltas` (keys self.rotk[delta] unless given): the ModUp
+        digits, extension and forward transform are computed once for all of them (tb200_rotate_hoisted).
+        An extension beyond the reference, whose rotate_offset / sum / BSGS loops call rotate_single per key
+        (ckks_engine.py:1908-1926, 2770-2788); each result decrypts like rotate_single(ct, rotk[delta])."""
+        deltas = list(deltas)
+        keys = [(rotks[d] if rotks is not None else self.rotk[d]) for d in deltas]
+        c0, c1 = self._t(ct.data[0]), self._t(ct.data[1])
+        o0 = torch.empty((len(deltas), *c0.shape), dtype=torch.int64, device=c0.device)
+        o1 = torch.empty_like(o0)
+        self.ctx.rotate_hoisted(ct.level, [galois_element(self.N, k.delta) for k in keys], c0, c1,
+                                [self._key(k) for k in keys], o0, o1)
+        return [Ciphertext(data=[[o0[r]], [o1[r]]], flags=ct._flags, level=ct.level, misc=dict(ct.misc))
+                for r in range(len(deltas))]
 
     # ---- add / sub -----------------------------------------------------------------------------
     def _addsub(self, a, b, sub):

@@ -397,6 +397,25 @@ class Tb200Context:
                                    _stream(out0))
         self.lib.check(rc, "rotate")
 
+    def rotate_hoisted(self, level: int, galois, c0, c1, rotks, out0, out1):
+        """Rotations galois[r] (keys rotks[r]) of the same ciphertext(s) with the ModUp shared (extension beyond
+        the reference, see include/tb200.h).  out0 / out1: [R, (B,) L, N] dense over the rotation axis."""
+        R = len(galois)
+        if len(rotks) != R or out0.shape[0] != R or out1.shape[0] != R:
+            raise Tb200Error("rotate_hoisted: one key and one output slice per rotation")
+        r = self._rows(level)
+        self._shapes("rotate_hoisted", level, ("c0", c0, r), ("c1", c1, r), ("out0", out0[0], r), ("out1", out1[0], r),
+                     key=rotks[0])
+        for k in rotks[1:]:
+            self._shapes("rotate_hoisted", level, key=k)
+        if _strides(out0)[0] != _strides(out1)[0]:
+            raise Tb200Error("rotate_hoisted: out0 and out1 need the same stride over the rotation axis")
+        g = (C.c_int64 * R)(*[int(x) for x in galois])
+        kp = (C.c_void_p * R)(*[C.cast(C.pointer(k.c), C.c_void_p) for k in rotks])
+        rc = self.lib.tb200_rotate_hoisted(self.h, level, self._batch(c0), R, g, self._pp(c0), self._pp(c1), kp,
+                                           self._pp(out0[0]), self._pp(out1[0]), _strides(out0)[0], _stream(out0))
+        self.lib.check(rc, "rotate_hoisted")
+
     def switch_key(self, level: int, c0, c1, ksk: KeySwitchKeyView, out0, out1):
         r = self._rows(level)
         self._shapes("switch_key", level, ("c0", c0, r), ("c1", c1, r), ("out0", out0, r), ("out1", out1, r), key=ksk)

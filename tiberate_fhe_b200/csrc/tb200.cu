@@ -1360,7 +1360,7 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
       // key inner product, 128-bit accumulation over the groups
       LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)(E - nf), 1u),
              dim3(N / 2 < 256 ? N / 2 : 256), sst, d, c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb,
-             ex ? ex->nadd0 : (const i64*)nullptr, ex ? ex->nadd1 : (const i64*)nullptr, (const i64*)c->d_cP, nf);
+             ex ? ex->nadd0 : (const i64*)nullptr, ex ? ex->nadd1 : (const i64*)nullptr, (const i64*)c->d_cP, nf, 0u);
       const TbView ar = rows_from(dense(acc, E, N), nf);
       if ((rc = launch_fast_B(c, true, ar, ar, E - nf, nb * 2, p0 + nf, sst, TB_INV_IN_DOUBLE))) return rc;
     }
@@ -1601,6 +1601,77 @@ extern "C" int tb200_rotate(tb200_ctx* c, int level, int batch, int64_t galois, 
     rc = keyswitch_chunk(c, level, nb, dense(r1, L, N), key, dense(r0, L, N), dense(r0, L, N), shift(view(out0), b0),
                          shift(view(out1), b0), 2, ksws, st);
     if (rc) return rc;
+  }
+  POST();
+  return 0;
+}
+
+// Hoisted rotations: `nrot` rotations of the SAME ciphertext(s) share the ModUp digits, the extension and its
+// forward transform; per rotation only the key inner product (reading the extension through the NTT-domain
+// automorphism), the inverse transform, ModDown and the coefficient-domain automorphism of c0 remain.
+//   out_r = (sigma_r(c0) + ks0_r, ks1_r),  ks_r = ModDown(sum_g sigma_r(NTT(ext_g)) (x) rotk_r[g]).
+// An extension beyond the reference (it rotates one key at a time, ckks_engine.py:1804-1840, 1908-1926): the result
+// decrypts to the same rotation as rotate_single but is NOT bit-identical to it (the digits are taken before the
+// automorphism, so negated coefficients lift to other representatives); oracle/engine.py: rotate_hoisted restates
+// it, tests compare bit for bit with that and decrypt.
+extern "C" int tb200_rotate_hoisted(tb200_ctx* c, int level, int batch, int nrot, const int64_t* galois,
+                                    const tb200_poly* c0, const tb200_poly* c1, const tb200_ksk* const* rotks,
+                                    const tb200_poly* out0, const tb200_poly* out1, int64_t rot_stride,
+                                    tb200_stream st) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  REQUIRE_UNSHARDED();
+  if (nrot < 1 || !galois || !rotks) return fail(TB200_EINVAL, "rotate_hoisted: need nrot >= 1, galois and keys");
+  if (!c->fast) return fail(TB200_EINVAL, "rotate_hoisted runs on the mod-q path (tb200_ctx_set_fast(ctx, 1))");
+  CHECK_POLY(c0);
+  CHECK_POLY(c1);
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  if (rot_stride & 1) return fail(TB200_EINVAL, "rotate_hoisted: rot_stride must be even");
+  std::vector<TbKskDev> keys(nrot);
+  for (int r = 0; r < nrot; ++r) {
+    if (!(galois[r] & 1) || galois[r] < 1 || galois[r] >= 2 * (int64_t)c->N)
+      return fail(TB200_EINVAL, "galois element %d must be odd and in [1, 2N)", r);
+    if ((rc = make_key(c, level, rotks[r], &keys[r]))) return rc;
+  }
+  SET_DEVICE(c->device);
+  const int N = c->N, L = c->num_ord - level, E = L + c->K;
+  const TbKsLevel& lv = c->ks[level];
+  const int ng = lv.ngroups, S = lv.state_rows;
+  const TbKsLevel* dlv = c->d_ks + level;
+  const int ch = batch < c->chunk ? batch : c->chunk;
+  WsLease ws(c, st);
+  if ((rc = ws.reserve((ks_ws_elems(c, level) + (size_t)L * N) * ch))) return rc;
+  for (int b0 = 0; b0 < batch; b0 += ch) {
+    const int nb = batch - b0 < ch ? batch - b0 : ch;
+    i64* state = ws.p;
+    i64* ext = state + (size_t)nb * S * N;
+    i64* acc = ext + (size_t)nb * ng * E * N;
+    i64* r0 = acc + (size_t)nb * 2 * E * N;
+    // once: digits, ModUp + forward transform of every group over all E limbs
+    if ((rc = ks_digits(c, level, nb, shift(view(c1), b0), dense(state, S, N), st))) return rc;
+    if ((rc = ks_modup(c, level, nb, dense(state, S, N), ext, st, false, 0))) return rc;
+    if ((rc = launch_fast_B(c, false, dense(ext, E, N), dense(ext, E, N), E, nb * ng, level, st, 0, nullptr, 1))) return rc;
+    for (int r = 0; r < nrot; ++r) {
+      LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)E, 1u), dim3(N / 2 < 256 ? N / 2 : 256), st,
+             c->dev(), c->devf(), dlv, keys[r], (const i64*)ext, acc, level, N, E, nb, (const i64*)nullptr,
+             (const i64*)nullptr, (const i64*)c->d_cP, 0, (unsigned)galois[r]);
+      if ((rc = fast_inverse_exit(c, dense(acc, E, N), dense(acc, E, N), E, nb * 2, level, st, 1))) return rc;
+      const dim3 gridb((unsigned)((N + 255) / 256), (unsigned)L, (unsigned)nb);
+      LAUNCH(k_automorphism, gridb, dim3(256), st, c->dev(), shift(view(c0), b0), dense(r0, L, N), level, (i64)galois[r]);
+      TbView o0 = shift(view(out0), b0), o1 = shift(view(out1), b0);
+      o0.p += (long)r * rot_stride;
+      o1.p += (long)r * rot_stride;
+      for (int h = 0; h < 2; ++h) {
+        TbView cc;
+        cc.p = acc + (size_t)h * E * N;
+        cc.bs = 2L * E * N;
+        cc.rs = N;
+        TbView p = cc;
+        p.p += (size_t)L * N;
+        if ((rc = moddown(c, level, nb, cc, p, dense(r0, L, N), h == 0 ? o0 : o1, h == 0 ? 2 : 0, st))) return rc;
+      }
+    }
   }
   POST();
   return 0;

@@ -504,9 +504,22 @@ __device__ __forceinline__ i64 tb_norm2q(i64 x, i64 q2) {
 // special primes, are added to the ordinary limbs of the two sums -- ModDown then returns ks + d exactly
 // ((x + P d - [x]_P) / P = (x - [x]_P) / P + d), so d0 and d1 need no inverse transform of their own.
 // cP: [2][nP] = P mod q (limbs whose sums carry no Montgomery factor: FP64 limbs) and P R mod q (others).
+// Galois automorphism X -> X^g in the NTT domain: slot i of the transform holds the evaluation at
+// psi^(2 brev(i) + 1), and (sigma_g a)(psi^e) = a(psi^(e g)), so slot i of sigma_g(a) is slot
+// brev(((2 brev(i) + 1) g mod 2N - 1) / 2) of a -- a pure permutation, no signs.  Aligned blocks of 2^k slots
+// map to aligned blocks (the low bits of brev(i) fix e modulo a power of two), in particular an aligned pair to
+// an aligned pair: gathered reads stay as coalesced as straight ones.
+__device__ __forceinline__ unsigned tb_ntt_slot_perm(unsigned i, unsigned g, int logN) {
+  const unsigned bi = __brev(i) >> (32 - logN);
+  const unsigned e = ((2u * bi + 1u) * g) & ((2u << logN) - 1u);
+  return __brev((e - 1u) >> 1) >> (32 - logN);
+}
+
+// galois != 0 (hoisted rotations): the extension limbs are read through the NTT-domain automorphism above.
 __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
                                                   const i64* ext, i64* acc, int level, int N, int rowsE, int nb,
-                                                  const i64* nadd0, const i64* nadd1, const i64* cP, int row0) {
+                                                  const i64* nadd0, const i64* nadd1, const i64* cP, int row0,
+                                                  unsigned galois) {
   // grid.x = nb * tiles with the batch index fastest: the nb ciphertexts of a chunk read the same key
   // tile back to back, so the key is fetched from HBM once per chunk (L2 serves the rest)
   const int t = row0 + blockIdx.y, bt = blockIdx.x % nb;
@@ -515,6 +528,23 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
   const int j = ((blockIdx.x / nb) * blockDim.x + threadIdx.x) * 2;
   if (j >= N) return;
   const int ng = lv->ngroups;
+  // source pair of the extension limbs: (j, j + 1) itself, or its image under the automorphism
+  int sj = j;
+  bool swp = false;
+  if (galois != 0) {
+    const unsigned pj = tb_ntt_slot_perm((unsigned)j, galois, f.logN);
+    sj = (int)(pj & ~1u);
+    swp = (pj & 1u) != 0;
+  }
+  auto ldext = [&](const i64* p) {
+    longlong2 v = *reinterpret_cast<const longlong2*>(p);
+    if (swp) {
+      const i64 tmp = v.x;
+      v.x = v.y;
+      v.y = tmp;
+    }
+    return v;
+  };
   longlong2 o0, o1;
   if (f.fp[level + t].f64) {
     // FP64 limbs: extensions are doubles (k_fast_fwd_B dbl_out / k_fast_own_fill), the key residues
@@ -532,12 +562,12 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
       s1x = pol.mulmod(tb::FastF64Pol::from_int(u1.x), F.cPd);
       s1y = pol.mulmod(tb::FastF64Pol::from_int(u1.y), F.cPd);
     }
-    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + j;
+    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + sj;
     const long estride = (long)rowsE * N, koff = (long)(level + t) * key.rs + j;
 #pragma unroll 2
     for (int gi = 0; gi < ng; ++gi) {
       const int gid = lv->g[gi].gid;
-      const longlong2 e = *reinterpret_cast<const longlong2*>(ep);
+      const longlong2 e = ldext(ep);
       const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + koff);
       const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + koff);
       ep += estride;
@@ -573,13 +603,13 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
     // Two digit groups per iteration so that six 16-byte loads are in flight per thread (the kernel
     // is latency-bound: ncu long_scoreboard 5.6 stalls per issue before the unroll)
     __int128 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
-    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + j;
+    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + sj;
     const long estride = (long)rowsE * N, koff = (long)(level + t) * key.rs + j;
     int gi = 0;
     for (; gi + 2 <= ng; gi += 2) {
       const int g0 = lv->g[gi].gid, g1 = lv->g[gi + 1].gid;
-      const longlong2 e0 = *reinterpret_cast<const longlong2*>(ep);
-      const longlong2 e1 = *reinterpret_cast<const longlong2*>(ep + estride);
+      const longlong2 e0 = ldext(ep);
+      const longlong2 e1 = ldext(ep + estride);
       const longlong2 kb0 = *reinterpret_cast<const longlong2*>(key.b[g0] + koff);
       const longlong2 ka0 = *reinterpret_cast<const longlong2*>(key.a[g0] + koff);
       const longlong2 kb1 = *reinterpret_cast<const longlong2*>(key.b[g1] + koff);
@@ -592,7 +622,7 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
     }
     if (gi < ng) {
       const int gid = lv->g[gi].gid;
-      const longlong2 e = *reinterpret_cast<const longlong2*>(ep);
+      const longlong2 e = ldext(ep);
       const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + koff);
       const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + koff);
       a0x += (__int128)e.x * kb.x;
@@ -608,7 +638,7 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
     i64 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
     for (int gi = 0; gi < ng; ++gi) {
       const int gid = lv->g[gi].gid;
-      const longlong2 e = *reinterpret_cast<const longlong2*>(ext + (((long)bt * ng + gi) * rowsE + t) * N + j);
+      const longlong2 e = ldext(ext + (((long)bt * ng + gi) * rowsE + t) * N + sj);
       const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + (long)(level + t) * key.rs + j);
       const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + (long)(level + t) * key.rs + j);
       a0x = tb_norm2q(a0x + tb_mm_ss(e.x, kb.x, P.q4, P.k), P.q2);

@@ -92,6 +92,11 @@ static inline double tb_rint(double a) { return std::nearbyint(a); }
 static inline unsigned __umulhi(unsigned a, unsigned b) {
   return (unsigned)(((unsigned long long)a * b) >> 32);
 }
+static inline unsigned __brev(unsigned x) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+  return r;
+}
 static inline long long __mul64hi(long long a, long long b) {
   return (long long)(((__int128)a * (__int128)b) >> 64);
 }
