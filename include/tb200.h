@@ -106,6 +106,20 @@ enum tb200_tuning { TB200_TUNE_FUSED_CORE = 0, TB200_TUNE_SIDE_ROWS = 1, TB200_T
                     TB200_TUNE_STREAM_WS = 3, TB200_TUNE_SUM_NTT = 4 };
 int tb200_ctx_set_tuning(tb200_ctx*, int knob, int value);
 
+/* ---- packed wire format ------------------------------------------------------------------------------
+ * Canonical residues of the scale primes (all within 2^32 of 2^40, i.e. below 2^41) as 41 bits each: a limb is
+ * 5 N bytes (bits 0..39 of residue j at byte 5 j, little endian) followed by N / 8 bytes (bit 40 of residue j = bit
+ * j % 8 of byte j / 8) -- 5.125 bytes per residue instead of the 8 of the int64 layout: what crosses the host <->
+ * device link (-36 % bytes on those limbs).  The `rows` limbs starting at prime index prime0 must all be below 2^41
+ * (wider limbs travel as int64).  Packed buffers: device memory, 8-byte aligned, strides in BYTES (multiples of 8,
+ * row pitch >= 5 N + N / 8), N >= 64.  tb200_pack41 expects canonical inputs (every engine call returns canonical
+ * residues); the reference has no equivalent (its ciphertexts leave the device only through pickle,
+ * tiberate/typing.py:283-290). */
+int tb200_unpack41(tb200_ctx*, int rows, int batch, int prime0, const uint8_t* src, int64_t src_batch_stride,
+                   int64_t src_row_stride, const tb200_poly* dst, tb200_stream);
+int tb200_pack41(tb200_ctx*, int rows, int batch, int prime0, const tb200_poly* src, uint8_t* dst,
+                 int64_t dst_batch_stride, int64_t dst_row_stride, tb200_stream);
+
 /* ---- op layer: pointwise Montgomery family (mont_cuda.cu, mont_extra_cuda.cu) ---------------- */
 enum tb200_pw_op {
   TB200_MONT_MULT = 0,          /* out = MM(a, b)                      mont_cuda.cu:11-36    */

@@ -63,6 +63,17 @@ def test_engine_every_level(h, logN, ns, K):
         s.close()
 
 
+def test_engine_logN12_compile_time_strides(h):
+    """logN >= 12 selects the instantiations the presets run: LB = 8, compile-time strides, FP64-only row launches
+    split from the integer rows, the fused key-switch core with its staged 4096-residue tiles."""
+    s = Setup.toy(h, 12, 2, 2, seed=312, rot_deltas=(1, 2))
+    try:
+        parity.check_engine(s, 0, ops=("cc_mult", "rotate", "hoisted", "keyswitch", "pc_mult"))
+        parity.check_engine(s, 1, batch=2, ops=("cc_mult", "rotate"))
+    finally:
+        s.close()
+
+
 def test_engine_wide_scale_primes(h):
     """55-bit "scale" primes: every limb takes the reducing (non-small) butterfly policy, with
     multi-prime digit groups."""
@@ -183,3 +194,42 @@ def test_limb_sharded_keyswitch_matches_single_device(h, world):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_packed_wire_format_roundtrip(h):
+    """tb200_pack41 / tb200_unpack41: 41 bits per residue (5 bytes + a bit plane), against a NumPy packing."""
+    import numpy as np
+
+    from tiberate_fhe_b200 import Tb200Error
+
+    s = Setup.toy(h, 8, 3, 1, seed=4)
+    try:
+        ctx, N = s.ctx, s.N
+        q = ctx.q
+        nar = ctx.narrow_rows(0, ctx.P)
+        assert nar == 3 and ctx.narrow_rows(1, 3) == 2 and ctx.packed_row_bytes == 5 * N + N // 8
+        rng = np.random.default_rng(0)
+        a = np.stack([np.stack([rng.integers(0, q[r], size=N, dtype=np.int64) for r in range(nar)]) for _ in range(2)])
+        a[0, 0, 0], a[1, 2, N - 1] = q[0] - 1, q[2] - 1
+        a[0, 1, 5] = (1 << 40) + 12345  # a residue that needs bit 40 (scale primes reach above 2^40)
+        a[1, 0, 8] = 1 << 40
+        packed = np.zeros((2, nar, ctx.packed_row_bytes), dtype=np.uint8)
+        ctx.pack41(a, packed, 0)
+
+        def ref_pack(row):
+            lo = (row & ((1 << 40) - 1)).astype("<u8").view(np.uint8).reshape(N, 8)[:, :5].reshape(-1)
+            hi = np.packbits(((row >> 40) & 1).astype(np.uint8), bitorder="little")
+            return np.concatenate([lo, hi])
+
+        ref = np.stack([np.stack([ref_pack(a[b, r]) for r in range(nar)]) for b in range(2)])
+        assert np.array_equal(packed, ref)
+        out = np.zeros_like(a)
+        ctx.unpack41(packed, out, 0)
+        assert np.array_equal(out, a)
+        one = np.zeros((nar - 1, N), dtype=np.int64)  # unbatched, rows 1..: a row-offset view of the packed buffer
+        ctx.unpack41(packed[1, 1:], one, 1)
+        assert np.array_equal(one, a[1, 1:])
+        with pytest.raises(Tb200Error, match="41 bits"):
+            ctx.pack41(np.zeros((4, N), dtype=np.int64), np.zeros((4, ctx.packed_row_bytes), dtype=np.uint8), 0)  # row 3: 60-bit prime
+    finally:
+        s.close()

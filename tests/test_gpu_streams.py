@@ -93,3 +93,28 @@ def test_current_device_is_restored():
     ctx.ntt(a, 0, True)
     assert torch.cuda.current_device() == 0
     ctx.close()
+
+
+def test_packed_wire_format_on_the_device():
+    import numpy as np
+    import torch
+
+    ctx, key, (a0, a1, b0, b1), no, N = _setup(torch, B=3)
+    nar = ctx.narrow_rows(0, no)
+    assert nar == no - 1  # every scale prime (40 or 41 bits), not the 60-bit base prime
+    wide = [r for r in range(nar) if ctx.q[r] >= (1 << 40)]
+    assert wide, "the preset has scale primes above 2^40"
+    for r in wide:  # residues that need bit 40
+        a0[0, r, 5] = ctx.q[r] - 1
+        a0[2, r, N - 1] = 1 << 40
+    packed = torch.empty(3, nar, ctx.packed_row_bytes, dtype=torch.uint8, device="cuda")
+    ctx.pack41(a0[:, :nar], packed, 0)
+    host = a0[:, :nar].cpu().numpy()
+    assert int((host >> 40).max()) == 1, "the preset has scale primes above 2^40: bit 40 must be exercised"
+    lo = (host & ((1 << 40) - 1)).astype("<u8").view(np.uint8).reshape(3, nar, N, 8)[..., :5].reshape(3, nar, 5 * N)
+    hi = np.packbits(((host >> 40) & 1).astype(np.uint8), axis=-1, bitorder="little")
+    assert (packed.cpu().numpy() == np.concatenate([lo, hi], axis=-1)).all()
+    back = torch.zeros(3, no, N, dtype=torch.int64, device="cuda")
+    ctx.unpack41(packed, back[:, :nar], 0)
+    assert torch.equal(back[:, :nar], a0[:, :nar])
+    ctx.close()

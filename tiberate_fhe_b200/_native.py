@@ -68,6 +68,8 @@ SIGNATURES = {
     "tb200_ks_digits": (_i, [_vp, _i, _i, PP, PP, _vp]),
     "tb200_ks_finish": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, PP, PP, _i, _vp]),
     "tb200_ks_modup": (_i, [_vp, _i, _i, PP, _i, _vp]),
+    "tb200_unpack41": (_i, [_vp, _i, _i, _i, _vp, C.c_int64, C.c_int64, PP, _vp]),
+    "tb200_pack41": (_i, [_vp, _i, _i, _i, PP, _vp, C.c_int64, C.c_int64, _vp]),
     "tb200_ks_core": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_mult_relin": (_i, [_vp, _i, _i, PP, PP, PP, PP, C.POINTER(Ksk), PP, PP, _i, _vp]),
     "tb200_cc_mult_triplet": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, PP, PP, _i, _vp]),

@@ -259,6 +259,42 @@ class Tb200Context:
         self.lib.check(rc, "divide_by_p")
         return out
 
+    # ---- packed wire format (include/tb200.h) --------------------------------------------------
+    def narrow_rows(self, prime0: int, rows: int) -> int:
+        """how many of the `rows` limbs starting at prime index prime0 are scale-prime limbs (below 2^41; a
+        prefix: the chain is [scale primes..., base, special...])"""
+        n = 0
+        while n < rows and self.q[prime0 + n] < (1 << 41):
+            n += 1
+        return n
+
+    @property
+    def packed_row_bytes(self) -> int:
+        """bytes of one packed limb: 5 N + N / 8 (include/tb200.h, packed wire format)"""
+        return 5 * self.N + self.N // 8
+
+    def unpack41(self, packed, dst, prime0: int):
+        """packed: uint8 [(B,) rows, packed_row_bytes] (last dim contiguous) -> dst int64 [(B,) rows, N]"""
+        rows, batch = dst.shape[-2], self._batch(dst)
+        if packed.shape[-1] != self.packed_row_bytes or packed.shape[-2] != rows or _strides(packed)[-1] != 1:
+            raise Tb200Error(f"unpack41: packed must be [.., {rows}, {self.packed_row_bytes}] bytes, got {tuple(packed.shape)}")
+        st = _strides(packed)
+        rc = self.lib.tb200_unpack41(self.h, rows, batch, prime0, _ptr(packed), st[0] if len(st) == 3 else 0, st[-2],
+                                     self._pp(dst), _stream(dst))
+        self.lib.check(rc, "unpack41")
+        return dst
+
+    def pack41(self, src, packed, prime0: int):
+        """src int64 [(B,) rows, N] canonical -> packed uint8 [(B,) rows, packed_row_bytes]"""
+        rows, batch = src.shape[-2], self._batch(src)
+        if packed.shape[-1] != self.packed_row_bytes or packed.shape[-2] != rows or _strides(packed)[-1] != 1:
+            raise Tb200Error(f"pack41: packed must be [.., {rows}, {self.packed_row_bytes}] bytes, got {tuple(packed.shape)}")
+        st = _strides(packed)
+        rc = self.lib.tb200_pack41(self.h, rows, batch, prime0, self._pp(src), _ptr(packed), st[0] if len(st) == 3 else 0,
+                                   st[-2], _stream(src))
+        self.lib.check(rc, "pack41")
+        return packed
+
     # ---- engine layer --------------------------------------------------------------------
     @staticmethod
     def _batch(x) -> int:

@@ -735,6 +735,44 @@ extern "C" int tb200_add_many(tb200_ctx* c, int pairwise, int K, int rows, int p
   return 0;
 }
 
+// ---- packed wire format (scale-prime limbs as 41 bits per residue) -------------------------------------------
+static int check_pack(const tb200_ctx* c, int rows, int batch, int prime0, const void* bytes, int64_t bs, int64_t rs) {
+  if (!c) return fail(TB200_EINVAL, "null context");
+  if (rows < 1 || prime0 < 0 || prime0 + rows > c->P) return fail(TB200_EINVAL, "pack41: rows outside the context's primes");
+  if (batch < 1 || !bytes) return fail(TB200_EINVAL, "pack41: bad batch / null buffer");
+  if (c->N < 64) return fail(TB200_EINVAL, "pack41: N must be >= 64");
+  if (((uintptr_t)bytes & 7) || (bs & 7) || (rs & 7) || rs < (int64_t)c->N * 5 + c->N / 8)
+    return fail(TB200_EINVAL, "pack41: packed buffer needs 8-byte alignment and a row pitch >= 5 N + N / 8 (multiple of 8)");
+  for (int r = 0; r < rows; ++r)
+    if (((u64)c->q[prime0 + r] >> 41) != 0)
+      return fail(TB200_EINVAL, "pack41: prime %d has more than 41 bits; such limbs travel as int64", prime0 + r);
+  return 0;
+}
+extern "C" int tb200_unpack41(tb200_ctx* c, int rows, int batch, int prime0, const uint8_t* src, int64_t src_batch_stride,
+                              int64_t src_row_stride, const tb200_poly* dst, tb200_stream st) {
+  int rc = check_pack(c, rows, batch, prime0, src, src_batch_stride, src_row_stride);
+  if (rc) return rc;
+  CHECK_POLY(dst);
+  SET_DEVICE(c->device);
+  LAUNCH(k_unpack41, dim3((unsigned)((c->N / 8 + 255) / 256), (unsigned)rows, (unsigned)batch),
+         dim3(c->N / 8 < 256 ? c->N / 8 : 256), st, (const unsigned char*)src, (long)src_batch_stride,
+         (long)src_row_stride, view(dst), c->N);
+  POST();
+  return 0;
+}
+extern "C" int tb200_pack41(tb200_ctx* c, int rows, int batch, int prime0, const tb200_poly* src, uint8_t* dst,
+                            int64_t dst_batch_stride, int64_t dst_row_stride, tb200_stream st) {
+  int rc = check_pack(c, rows, batch, prime0, dst, dst_batch_stride, dst_row_stride);
+  if (rc) return rc;
+  CHECK_POLY(src);
+  SET_DEVICE(c->device);
+  LAUNCH(k_pack41, dim3((unsigned)((c->N / 8 + 255) / 256), (unsigned)rows, (unsigned)batch),
+         dim3(c->N / 8 < 256 ? c->N / 8 : 256), st, view(src), (unsigned char*)dst, (long)dst_batch_stride,
+         (long)dst_row_stride, c->N);
+  POST();
+  return 0;
+}
+
 // ---- NTT ----------------------------------------------------------------------------------------
 static inline int ntt_lw(const tb200_ctx* c) {  // log2 of the column width of a pass-A tile
   int lw = 12 - c->LA;
@@ -1071,14 +1109,38 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
   a.prime0 = prime0;
   a.ngroups = 1;
   int rc;
+  // the FP64 rows take the instantiation without the integer butterflies (64 registers, 4 CTAs per SM), the
+  // remaining rows the generic one -- as for pass B and the ModUp launch
+  const int nf = (c->LB == 8 && ntt_lw(c) == 12 - c->LA) ? f64_prefix(c, prime0, rows) : 0;
   if (rescale_level >= 0) {
     a.resc = c->d_resc3 + ((size_t)rescale_level * c->P + rescale_level + 1) * 3;
     a.round_at = (i64)(c->q[rescale_level] / 2);
-    rc = launch_fast_fwd_A<TB_FPRO_RESCALE_ENTER>(c, a, rows, batch, st);
-  } else {
-    rc = launch_fast_fwd_A<TB_FPRO_ENTER>(c, a, rows, batch, st);
+    if (nf > 0) {
+      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_RESCALE_ENTER, true>(c, a, nf, batch, st))) return rc;
+      if (nf < rows) {
+        // rows nf..: the dropped limb stays row 0 of the source, so the body rows are addressed through `row_shift`
+        TbFwdAArgs b = a;
+        b.prime0 += nf;
+        b.dst = rows_from(b.dst, nf);
+        b.resc += 3 * (size_t)nf;
+        b.row_shift = nf;
+        if ((rc = launch_fast_fwd_A_rows<TB_FPRO_RESCALE_ENTER, false>(c, b, rows - nf, batch, st))) return rc;
+      }
+    } else if ((rc = launch_fast_fwd_A<TB_FPRO_RESCALE_ENTER>(c, a, rows, batch, st))) {
+      return rc;
+    }
+  } else if (nf > 0) {
+    if ((rc = launch_fast_fwd_A_rows<TB_FPRO_ENTER, true>(c, a, nf, batch, st))) return rc;
+    if (nf < rows) {
+      TbFwdAArgs b = a;
+      b.prime0 += nf;
+      b.dst = rows_from(b.dst, nf);
+      b.row_shift = nf;
+      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_ENTER, false>(c, b, rows - nf, batch, st))) return rc;
+    }
+  } else if ((rc = launch_fast_fwd_A<TB_FPRO_ENTER>(c, a, rows, batch, st))) {
+    return rc;
   }
-  if (rc) return rc;
   return launch_fast_B(c, false, dst, dst, rows, batch, prime0, st);
 }
 // mac_chain: the input is the output of k_fast_mac, whose FP64 limbs are doubles

@@ -225,25 +225,36 @@ struct ExactSumPol {
   }
 };
 
-// any q < 2^60: Harvey lazy butterflies, forward values in [0, 4q), inverse values in [0, 2q).
+// any q < 2^60: Harvey butterflies with the lazy Shoup quotient (short by at most 2: products in [0, 4q)).
+// Forward: inputs below 8q; U is brought below 4q, outputs below 8q < 2^63.  Inverse: values below 4q.
 struct FastBigPol {
   u64 q, q2;
   typedef TbTw2 TW;
   typedef TbTw2 TWS;
   static __device__ __forceinline__ TW load(const TWS* t) { return load_tw2(t); }
   __device__ __forceinline__ void ct(i64& U, i64& O, TW S, int) const {
+    const u64 q4 = q2 + q2;
     u64 u = (u64)U;
-    u = (u >= q2) ? u - q2 : u;
-    const u64 v = shoup((u64)O, S.w, S.ws, q);
+    u = (u >= q4) ? u - q4 : u;
+    const u64 v = shoup_lazy((u64)O, S.w, S.ws, q);  // < 4q for any 64-bit O
     U = (i64)(u + v);
-    O = (i64)(u + q2 - v);
+    O = (i64)(u + q4 - v);
   }
   __device__ __forceinline__ void gs(i64& U, i64& V, TW S, int) const {
+    const u64 q4 = q2 + q2;
     const u64 u = (u64)U, v = (u64)V;
     u64 a = u + v;
-    a = (a >= q2) ? a - q2 : a;
+    a = (a >= q4) ? a - q4 : a;
     U = (i64)a;
-    V = (i64)shoup(u + q2 - v, S.w, S.ws, q);
+    V = (i64)shoup_lazy(u + q4 - v, S.w, S.ws, q);
+  }
+  // forward output (< 8q) -> [0, 2q)
+  __device__ __forceinline__ i64 reduce2q(i64 x) const {
+    const u64 q4 = q2 + q2;
+    u64 y = (u64)x;
+    y = (y >= q4) ? y - q4 : y;
+    y = (y >= q2) ? y - q2 : y;
+    return (i64)y;
   }
 };
 

@@ -140,6 +140,66 @@ __global__ void __launch_bounds__(256) k_pointwise(TbDev c, TbPwArgs g) {
   }
 }
 
+// ---- packed wire format of the scale-prime limbs ------------------------------------------------------------
+// The scale primes lie within 2^32 of 2^40, on both sides, so a canonical residue needs 41 bits; the int64 layout
+// moves 64.  On the host <-> device link (PCIe, the bound of every end-to-end figure) a limb travels as
+//     N x 5 bytes  (bits 0..39 of residue j at byte 5 j, little endian)  +  N / 8 bytes  (bit 40 of residue j = bit
+//     j % 8 of byte j / 8)                                                           = 5.125 bytes per residue.
+// A thread converts 8 residues = five 8-byte words + one byte <-> eight int64.
+__global__ void __launch_bounds__(256) k_unpack41(const unsigned char* src, long src_bs, long src_rs, TbView dst, int N) {
+  const int r = blockIdx.y, bt = blockIdx.z;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (j >= N) return;
+  const unsigned char* row = src + (long)bt * src_bs + (long)r * src_rs;
+  const u64* p = reinterpret_cast<const u64*>(row + (long)j * 5);
+  u64 w[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) w[i] = p[i];
+  const u64 hb = row[(long)N * 5 + (j >> 3)];
+  i64* d = dst.row(bt, r) + j;
+  const u64 M = (1ull << 40) - 1;
+  u64 v[8];
+  v[0] = w[0] & M;
+  v[1] = ((w[0] >> 40) | (w[1] << 24)) & M;
+  v[2] = (w[1] >> 16) & M;
+  v[3] = ((w[1] >> 56) | (w[2] << 8)) & M;
+  v[4] = ((w[2] >> 32) | (w[3] << 32)) & M;
+  v[5] = (w[3] >> 8) & M;
+  v[6] = ((w[3] >> 48) | (w[4] << 16)) & M;
+  v[7] = w[4] >> 24;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    longlong2 o;
+    o.x = (i64)(v[i] | (((hb >> i) & 1ull) << 40));
+    o.y = (i64)(v[i + 1] | (((hb >> (i + 1)) & 1ull) << 40));
+    *reinterpret_cast<longlong2*>(d + i) = o;
+  }
+}
+__global__ void __launch_bounds__(256) k_pack41(TbView src, unsigned char* dst, long dst_bs, long dst_rs, int N) {
+  const int r = blockIdx.y, bt = blockIdx.z;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (j >= N) return;
+  const i64* s = src.row(bt, r) + j;
+  const u64 M = (1ull << 40) - 1;
+  u64 v[8], hb = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const longlong2 t = *reinterpret_cast<const longlong2*>(s + i);
+    hb |= (((u64)t.x >> 40) & 1ull) << i;
+    hb |= (((u64)t.y >> 40) & 1ull) << (i + 1);
+    v[i] = (u64)t.x & M;
+    v[i + 1] = (u64)t.y & M;
+  }
+  unsigned char* row = dst + (long)bt * dst_bs + (long)r * dst_rs;
+  u64* p = reinterpret_cast<u64*>(row + (long)j * 5);
+  p[0] = v[0] | (v[1] << 40);
+  p[1] = (v[1] >> 24) | (v[2] << 16) | (v[3] << 56);
+  p[2] = (v[3] >> 8) | (v[4] << 32);
+  p[3] = (v[4] >> 32) | (v[5] << 8) | (v[6] << 48);
+  p[4] = (v[6] >> 16) | (v[7] << 24);
+  row[(long)N * 5 + (j >> 3)] = (unsigned char)hb;
+}
+
 // mont_(reduce_)add_many_3d: in [K][rows][N] dense -> out [rows][N]
 __global__ void __launch_bounds__(256) k_add_many(TbDev c, const i64* in, i64* out, int K, int rows, int N,
                                                   int prime0, int pairwise) {

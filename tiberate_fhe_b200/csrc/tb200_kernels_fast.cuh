@@ -46,6 +46,7 @@ struct TbFwdAArgs {
   const double* lenterd;  // EXTEND, FP64 limbs: L_{k-1} mod q centred (no Montgomery factor), same indexing
   int prime0, LW, ngroups;
   int skip_own;           // EXTEND: the (group, own limb) pairs were pre-filled by k_fast_own_fill
+  int row_shift;          // ENTER / RESCALE_ENTER: source row of limb 0 of this launch (row split of one tensor)
   int sel;                // EXTEND: 0 = every group, 1 = the groups this rank owns, 2 = the other ranks' groups
   int nsel;               // EXTEND: number of selected groups (grid.z = batch * nsel)
 };
@@ -54,11 +55,11 @@ template <int PRO>
 __device__ __forceinline__ i64 fast_prologue(const TbFwdAArgs& a, const TbFastPrime& P, int bt, int gi, int limb,
                                              unsigned col_off, int g, int nP) {
   if constexpr (PRO == TB_FPRO_ENTER) {
-    const i64 v = a.src.row(bt, limb)[col_off];
+    const i64 v = a.src.row(bt, limb + a.row_shift)[col_off];
     return (i64)(P.small ? tb::shoup_lazy((u64)(v + (i64)P.q), P.Rm, P.Rm_s, P.q)
                          : tb::shoup((u64)(v + (i64)P.q), P.Rm, P.Rm_s, P.q));
   } else if constexpr (PRO == TB_FPRO_RESCALE_ENTER) {
-    const i64 v = a.src.row(bt, limb + 1)[col_off];
+    const i64 v = a.src.row(bt, limb + a.row_shift + 1)[col_off];
     const i64 r = a.src.row(bt, 0)[col_off];
     const u64* c = a.resc + 3 * limb;
     const u64 t = (u64)(v - r + (i64)c[2]);
@@ -186,7 +187,8 @@ __device__ __forceinline__ void extend_prologue_f64(i64 (&x)[16], const TbFwdAAr
 // address arithmetic).
 // F64ONLY: every limb row of the launch takes the FP64 route (launcher splits the rows as for pass B).
 template <int LA, int PRO, bool BIG, bool F64ONLY = false>
-__global__ void __launch_bounds__(256, F64ONLY ? TB_F64A_MINB : (PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3))
+__global__ void __launch_bounds__(256, F64ONLY ? (PRO == TB_FPRO_EXTEND ? TB_F64A_MINB : TB_F64_MINB)
+                                                : (PRO == TB_FPRO_EXTEND ? TB_EXT_MINB : 3))
     k_fast_fwd_A(TbDevFast c, TbFwdAArgs a) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
   const int LB = BIG ? 8 : c.LB, LW = BIG ? 12 - LA : a.LW;
@@ -286,9 +288,10 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(T
       if (P.small) {
         tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastSmallPol{P.q, P.q2, c.logN}, slot);
       } else {
-        tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, tb::FastBigPol{P.q, P.q2}, slot);
+        const tb::FastBigPol bp{P.q, P.q2};
+        tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, tw, bp, slot);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = ((u64)x[i] >= P.q2) ? (i64)((u64)x[i] - P.q2) : x[i];
+        for (int i = 0; i < 16; ++i) x[i] = bp.reduce2q(x[i]);
       }
     }
     // final layout (field 0): a thread owns 16 consecutive residues.  Storing them directly would make
@@ -683,18 +686,40 @@ __global__ void __launch_bounds__(256) k_fast_divide_by_p(TbDevFast f, TbView cc
   const u64* b = bn + 2 * g;
   const longlong2 cv = *reinterpret_cast<const longlong2*>(cc.row(bt, r) + j);
   const u64* bk = b + 2 * (long)K * f.P;
-  u64 x0 = tb::shoup((u64)(cv.x + (i64)P.q), bk[0], bk[1], P.q);
-  u64 x1 = tb::shoup((u64)(cv.y + (i64)P.q), bk[0], bk[1], P.q);
-  for (int k = 0; k < K; ++k) {
-    const longlong2 pv = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
-    const u64* bb = b + 2 * (long)k * f.P;
-    x0 += tb::shoup((u64)(pv.x + (i64)P.off), bb[0], bb[1], P.q);
-    x1 += tb::shoup((u64)(pv.y + (i64)P.off), bb[0], bb[1], P.q);
-    x0 = (x0 >= P.q2) ? x0 - P.q2 : x0;
-    x1 = (x1 >= P.q2) ? x1 - P.q2 : x1;
+  i64 y0, y1;
+  if (P.small) {
+    // 40-bit limbs: lazy Shoup quotients (every term below 4q), no reduction between the K + 1 terms
+    // (sum < 4 (K + 1) q < 2^46), one exact reduction at the end on the FP64 pipe
+    u64 x0 = tb::shoup_lazy((u64)(cv.x + (i64)P.q), bk[0], bk[1], P.q);
+    u64 x1 = tb::shoup_lazy((u64)(cv.y + (i64)P.q), bk[0], bk[1], P.q);
+    for (int k = 0; k < K; ++k) {
+      const longlong2 pv = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
+      const u64* bb = b + 2 * (long)k * f.P;
+      x0 += tb::shoup_lazy((u64)(pv.x + (i64)P.off), bb[0], bb[1], P.q);
+      x1 += tb::shoup_lazy((u64)(pv.y + (i64)P.off), bb[0], bb[1], P.q);
+    }
+    const tb::FastF64Pol pol{P.qd, P.qinv};
+    double r0 = pol.reduce(tb::FastF64Pol::from_int((i64)x0)), r1 = pol.reduce(tb::FastF64Pol::from_int((i64)x1));
+    r0 = r0 < 0.0 ? __dadd_rn(r0, pol.q) : r0;
+    r1 = r1 < 0.0 ? __dadd_rn(r1, pol.q) : r1;
+    r0 = r0 >= pol.q ? __dadd_rn(r0, -pol.q) : r0;
+    r1 = r1 >= pol.q ? __dadd_rn(r1, -pol.q) : r1;
+    y0 = tb::FastF64Pol::to_int(r0);
+    y1 = tb::FastF64Pol::to_int(r1);
+  } else {
+    u64 x0 = tb::shoup((u64)(cv.x + (i64)P.q), bk[0], bk[1], P.q);
+    u64 x1 = tb::shoup((u64)(cv.y + (i64)P.q), bk[0], bk[1], P.q);
+    for (int k = 0; k < K; ++k) {
+      const longlong2 pv = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
+      const u64* bb = b + 2 * (long)k * f.P;
+      x0 += tb::shoup((u64)(pv.x + (i64)P.off), bb[0], bb[1], P.q);
+      x1 += tb::shoup((u64)(pv.y + (i64)P.off), bb[0], bb[1], P.q);
+      x0 = (x0 >= P.q2) ? x0 - P.q2 : x0;
+      x1 = (x1 >= P.q2) ? x1 - P.q2 : x1;
+    }
+    y0 = (i64)(x0 >= P.q ? x0 - P.q : x0);
+    y1 = (i64)(x1 >= P.q ? x1 - P.q : x1);
   }
-  i64 y0 = (i64)(x0 >= P.q ? x0 - P.q : x0);
-  i64 y1 = (i64)(x1 >= P.q ? x1 - P.q : x1);
   if constexpr (TAIL != 0) {
     const longlong2 av = *reinterpret_cast<const longlong2*>(add.row(bt, r) + j);
     if constexpr (TAIL == 1) {
