@@ -339,7 +339,10 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
         for (int kk = 0; kk < K; ++kk) pp = h_mulmod(pp, (u64)q[no + kk] % qi, qi);
         f.cPd = pp > qi / 2 ? -(double)(qi - pp) : (double)pp;
       }
-      f.pad0_ = 0.0;
+      {
+        const u64 ni = h_invmod_prime((u64)N, qi);
+        f.nid = ni > qi / 2 ? -(double)(qi - ni) : (double)ni;
+      }
     }
   }
   // rescale scales and P_k^-1 tables
@@ -805,14 +808,19 @@ static int launch_fwd_A(const tb200_ctx* c, TbView src, TbView dst, int rows, in
   return 0;
 }
 template <int EPI>
-static int launch_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, tb200_stream st) {
+static int launch_inv_A(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, tb200_stream st,
+                        unsigned char* flags = nullptr) {
   const int lw = ntt_lw(c);
   const dim3 grid((unsigned)(1 << (c->LB - lw)), (unsigned)rows, (unsigned)batch), block(1u << (c->LA - 4 + lw));
   switch (c->LA) {
 #define ACASE(n)                                            \
   case n: {                                                 \
+    if (flags) {                                            \
+      auto ksum = k_ntt_inv_A_sum<n, EPI>;                  \
+      LAUNCHN("k_ntt_inv_A_sum", ksum, grid, block, st, c->dev(), src, dst, prime0, lw, flags); \
+    }                                                       \
     auto kfn = k_ntt_inv_A<n, EPI>;                         \
-    LAUNCHN("k_ntt_inv_A", kfn, grid, block, st, c->dev(), src, dst, prime0, lw); \
+    LAUNCHN("k_ntt_inv_A", kfn, grid, block, st, c->dev(), src, dst, prime0, lw, (const unsigned char*)flags); \
   } break;
     ACASE(4) ACASE(5) ACASE(6) ACASE(7) ACASE(8) ACASE(9)
 #undef ACASE
@@ -829,8 +837,12 @@ static int launch_B(const tb200_ctx* c, bool inverse, TbView src, TbView dst, in
 #define BCASE(n)                                                 \
   case n: {                                                      \
     if (inverse) {                                               \
+      if (flags) {                                               \
+        auto ksum = k_ntt_inv_B_sum<n>;                          \
+        LAUNCHN("k_ntt_inv_B_sum", ksum, grid, block, st, c->dev(), src, dst, prime0, flags); \
+      }                                                          \
       auto kfn = k_ntt_inv_B<n>;                                 \
-      LAUNCHN("k_ntt_inv_B", kfn, grid, block, st, c->dev(), src, dst, prime0);  \
+      LAUNCHN("k_ntt_inv_B", kfn, grid, block, st, c->dev(), src, dst, prime0, (const unsigned char*)flags);  \
     } else {                                                     \
       if (flags) {                                               \
         auto ksum = k_ntt_fwd_B_sum<n>;                          \
@@ -861,19 +873,22 @@ static int ntt_forward(const tb200_ctx* c, TbView src, TbView dst, int rows, int
   if (rc) return rc;
   return launch_B(c, false, dst, dst, rows, batch, prime0, st, flags ? flags + ntt_tiles(c, rows, batch) : nullptr);
 }
+static size_t ntt_tiles(const tb200_ctx* c, int rows, int batch);
+// flags: 2 * ntt_tiles zeroed bytes (deferred-reduction kernels first, the generic ones on the flagged tiles) or nullptr
 static int ntt_inverse(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0, int mode,
-                       tb200_stream st) {
-  int rc = launch_B(c, true, src, dst, rows, batch, prime0, st);
+                       tb200_stream st, unsigned char* flags = nullptr) {
+  int rc = launch_B(c, true, src, dst, rows, batch, prime0, st, flags);
   if (rc) return rc;
+  unsigned char* fa = flags ? flags + ntt_tiles(c, rows, batch) : nullptr;
   switch (mode) {
     case 0:
-      return launch_inv_A<TB_EPI_NINV>(c, dst, dst, rows, batch, prime0, st);
+      return launch_inv_A<TB_EPI_NINV>(c, dst, dst, rows, batch, prime0, st, fa);
     case 1:
-      return launch_inv_A<TB_EPI_EXIT>(c, dst, dst, rows, batch, prime0, st);
+      return launch_inv_A<TB_EPI_EXIT>(c, dst, dst, rows, batch, prime0, st, fa);
     case 2:
-      return launch_inv_A<TB_EPI_EXIT_REDUCE>(c, dst, dst, rows, batch, prime0, st);
+      return launch_inv_A<TB_EPI_EXIT_REDUCE>(c, dst, dst, rows, batch, prime0, st, fa);
     case 3:
-      return launch_inv_A<TB_EPI_EXIT_SIGNED>(c, dst, dst, rows, batch, prime0, st);
+      return launch_inv_A<TB_EPI_EXIT_SIGNED>(c, dst, dst, rows, batch, prime0, st, fa);
   }
   return fail(TB200_EINVAL, "intt mode %d", mode);
 }
@@ -915,8 +930,21 @@ extern "C" int tb200_intt(tb200_ctx* c, int rows, int batch, int prime0, const t
   // intt_radix2_exit_reduce returns canonical residues, so the mod-q transforms give the same bits
   // (domain: |x| < 2^51 on the FP64 limbs, (-2q, 2q) elsewhere -- every lazy value the ops produce;
   // tb200_ctx_set_fast(ctx, 0) selects the reference's own butterflies for anything wider)
-  int rc = (c->fast && mode == 2) ? fast_inverse_exit(c, view(a), view(a), rows, batch, prime0, st, 0, true)
-                                  : ntt_inverse(c, view(a), view(a), rows, batch, prime0, mode, st);
+  int rc = 0;
+  if (c->fast && mode == 2) {
+    rc = fast_inverse_exit(c, view(a), view(a), rows, batch, prime0, st, 0, true);
+  } else {
+    // the lazy exits (stay in Montgomery form / exit / signed): deferred-reduction kernels on the 40-bit limbs
+    WsLease ws(c, st);
+    unsigned char* flags = nullptr;
+    if (c->fast && c->sum_ntt) {
+      const size_t nbytes = 2 * ntt_tiles(c, rows, batch);
+      if ((rc = ws.reserve((nbytes + 7) / 8))) return rc;
+      flags = reinterpret_cast<unsigned char*>(ws.p);
+      CK(cudaMemsetAsync(flags, 0, nbytes, (cudaStream_t)st));
+    }
+    rc = ntt_inverse(c, view(a), view(a), rows, batch, prime0, mode, st, flags);
+  }
   if (rc) return rc;
   POST();
   return 0;

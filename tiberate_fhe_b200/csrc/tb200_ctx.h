@@ -127,6 +127,7 @@ struct tb200_ctx {
     d.P = P;
     d.fp = d_fp;
     d.twd = d_twd;
+    d.itwd = d_itwd;
     d.x64 = fast;
     return d;
   }

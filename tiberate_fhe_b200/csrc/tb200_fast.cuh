@@ -31,7 +31,7 @@ struct __align__(16) TbFastPrime {
   int small;         // q < 2^42
   int f64;           // small prime whose butterflies run on the FP64 pipe (see FastF64Pol)
   double qd, qinv;   // q and 1/q as doubles
-  double exd, pad0_;  // ex centred into (-q/2, q/2]
+  double exd, nid;   // ex and N^-1 mod q, centred into (-q/2, q/2]
   double Rcd, cPd;   // R mod q and P mod q (P = product of the special primes) centred
 };
 
@@ -216,7 +216,31 @@ struct ExactSumPol {
     Ub = __double_as_longlong(__dadd_rn(U, V));
     Ob = __double_as_longlong(__dadd_rn(U, -V));
   }
-  // T -> T mod 2q in [0, 2q), as an integer
+  // Gentleman-Sande (inverse) butterfly, same idea: lo = CS2(U + V) is (U + V) mod 2q, and hi = MM(S, CS2(U + 2q - V))
+  // depends on U - V only modulo q outside the band, where it is the canonical residue.  The lo path doubles per
+  // stage (|T| < 2q 2^8 per pass), the hi output restarts in [0, q).
+  __device__ __forceinline__ void gs(i64& Ub, i64& Vb, TW w, int) const {
+    const double U = __longlong_as_double(Ub), V = __longlong_as_double(Vb);
+    double r = f.mulmod(__dadd_rn(U, -V), w);
+    const unsigned hi = (unsigned)((u64)__double_as_longlong(r) >> 32);
+    *minhi = min(*minhi, hi & 0x7fffffffu);
+    r = (hi >> 31) ? __dadd_rn(r, f.q) : r;
+    Ub = __double_as_longlong(__dadd_rn(U, V));
+    Vb = __double_as_longlong(r);
+  }
+  // MM(y, c R) for a lazy y in [0, 2q) and a canonical constant: the canonical residue of y c outside the band
+  __device__ __forceinline__ double scale(double y, double c_centred) const {
+    double r = f.mulmod(y, c_centred);
+    const unsigned hi = (unsigned)((u64)__double_as_longlong(r) >> 32);
+    *minhi = min(*minhi, hi & 0x7fffffffu);
+    return (hi >> 31) ? __dadd_rn(r, f.q) : r;
+  }
+  // T -> T mod 2q in [0, 2q), as a double / as an integer
+  __device__ __forceinline__ double finish_d(i64 Tb) const {
+    const double T = __longlong_as_double(Tb);
+    const double y = __fma_rn(-FastF64Pol::round_int(__fma_rn(T, inv2q, TB_F64_MAGIC)), q2, T);
+    return y < 0.0 ? __dadd_rn(y, q2) : y;
+  }
   __device__ __forceinline__ i64 finish(i64 Tb) const {
     const double T = __longlong_as_double(Tb);
     double y = __fma_rn(-FastF64Pol::round_int(__fma_rn(T, inv2q, TB_F64_MAGIC)), q2, T);

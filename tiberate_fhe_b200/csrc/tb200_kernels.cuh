@@ -28,6 +28,7 @@ struct TbDev {
   // (ExactF64Pol): enabled per context, per prime by TbFastPrime.f64
   const TbFastPrime* fp;
   const double* twd;
+  const double* itwd;  // inverse twiddles, centred doubles (deferred-reduction inverse kernels)
   int x64;
 };
 
@@ -475,8 +476,9 @@ __global__ void __launch_bounds__(256, 4) k_ntt_fwd_B_sum(TbDev c, TbView src, T
 
 // inverse pass B': inverse stages 0..LB-1 (distances 1..2^(LB-1)) on contiguous blocks.
 template <int LB>
-__global__ void __launch_bounds__(256) k_ntt_inv_B(TbDev c, TbView src, TbView dst, int prime0) {
+__global__ void __launch_bounds__(256) k_ntt_inv_B(TbDev c, TbView src, TbView dst, int prime0, const unsigned char* todo) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  if (todo != nullptr && todo[tile_flag_index()] == 0) return;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int limb = blockIdx.y, g = prime0 + limb;
   const tb::PrimeRegs p = load_prime(c.pr, g);
@@ -513,8 +515,10 @@ __device__ __forceinline__ i64 intt_epilogue(i64 x, i64 Ninv, const tb::PrimeReg
 
 // inverse pass A': inverse stages LB..logN-1 on 2^LA rows x W columns, then the N^-1 epilogue.
 template <int LA, int EPI>
-__global__ void __launch_bounds__(256) k_ntt_inv_A(TbDev c, TbView src, TbView dst, int prime0, int LW) {
+__global__ void __launch_bounds__(256) k_ntt_inv_A(TbDev c, TbView src, TbView dst, int prime0, int LW,
+                                                   const unsigned char* todo) {
   TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  if (todo != nullptr && todo[tile_flag_index()] == 0) return;
   const int W = 1 << LW;
   const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
   const int limb = blockIdx.y, g = prime0 + limb;
@@ -530,6 +534,107 @@ __global__ void __launch_bounds__(256) k_ntt_inv_A(TbDev c, TbView src, TbView d
   const i64 Ninv = c.pr[g].Ninv;
 #pragma unroll
   for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, f0) << c.LB] = intt_epilogue<EPI>(x[i], Ninv, p);
+}
+
+// ---- deferred-reduction inverse transforms (ExactSumPol::gs), all four exits --------------------------------
+// As the forward pair: FP64 limbs with lazy inputs in [0, 2q) only; other tiles are flagged for the generic kernels.
+template <int LB>
+__global__ void __launch_bounds__(256, 4) k_ntt_inv_B_sum(TbDev c, TbView src, TbView dst, int prime0,
+                                                          unsigned char* todo) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime& F = c.fp[g];
+  if (!c.x64 || !F.f64) {
+    if (tid == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+  const long e0 = (long)blockIdx.x * nt * 16;
+  const i64* s = src.row(blockIdx.z, limb) + e0;
+  i64* d = dst.row(blockIdx.z, limb) + e0;
+  const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
+  const int tile = (int)(e0 >> LB) + blk;
+  auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
+  constexpr int f0 = tb::fwd_field<LB>(0);
+  // coalesced 128-bit loads, transposed through shared memory into the field-0 layout (as k_fast_inv_B)
+  const longlong2* sv = reinterpret_cast<const longlong2*>(s);
+  bool bad = false;
+  const i64 hi = (i64)(2 * F.q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const longlong2 v = sv[i * nt + tid];
+    const int e = 2 * (i * nt + tid);
+    bad |= (v.x < 0) | (v.x >= hi) | (v.y < 0) | (v.y >= hi);
+    sm[tb::pad16(e)] = v.x;
+    sm[tb::pad16(e + 1)] = v.y;
+  }
+  __syncthreads();
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __double_as_longlong(tb::FastF64Pol::from_int(sm[slot(tb::tile_x(lt, i, 0))]));
+  unsigned minhi = 0x7fffffffu;
+  const tb::ExactSumPol sp = exact_sum_policy(c, g, &minhi);
+  const unsigned band_hi = (unsigned)((u64)__double_as_longlong(sp.xbmax) >> 32) + 1u;
+  tb::tile_inv<LB, true>(x, sm, lt, tile, c.logN - 1, c.itwd + ((long)g << c.logN), sp, slot);
+  if (tb_block_any(bad | (minhi < band_hi))) {
+    if (tid == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[(blk << LB) | tb::tile_x(lt, i, f0)] = sp.finish(x[i]);
+}
+
+template <int LA, int EPI>
+__global__ void __launch_bounds__(256, 4) k_ntt_inv_A_sum(TbDev c, TbView src, TbView dst, int prime0, int LW,
+                                                          unsigned char* todo) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int W = 1 << LW;
+  const int col = threadIdx.x & (W - 1), tr = threadIdx.x >> LW;
+  const int limb = blockIdx.y, g = prime0 + limb;
+  const TbFastPrime& F = c.fp[g];
+  if (!c.x64 || !F.f64) {
+    if (threadIdx.x == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+  const i64* s = src.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  i64* d = dst.row(blockIdx.z, limb) + (long)blockIdx.x * W + col;
+  constexpr int f0 = tb::fwd_field<LA>(0);
+  i64 x[16];
+  bool bad = false;
+  const i64 hi = (i64)(2 * F.q);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const i64 v = s[(long)tb::tile_x(tr, i, 0) << c.LB];
+    bad |= (v < 0) | (v >= hi);
+    x[i] = __double_as_longlong(tb::FastF64Pol::from_int(v));
+  }
+  unsigned minhi = 0x7fffffffu;
+  const tb::ExactSumPol sp = exact_sum_policy(c, g, &minhi);
+  const unsigned band_hi = (unsigned)((u64)__double_as_longlong(sp.xbmax) >> 32) + 1u;
+  auto slot = [&](int lx) { return tb::pad16((lx << LW) | col); };
+  tb::tile_inv<LA>(x, sm, tr, 0, LA - 1, c.itwd + ((long)g << c.logN), sp, slot);
+  // epilogue (intt_epilogue): MM(y, N^-1 R) is the canonical residue of y N^-1 outside the band; MR of a canonical
+  // residue is the canonical residue of its product with R^-1; then CS1 / make_signed act on canonical values
+  double r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    double v = sp.scale(sp.finish_d(x[i]), F.nid);  // EPI NINV: stays in Montgomery form
+    if constexpr (EPI >= TB_EPI_EXIT) {
+      // MR(v) = v R^-1 mod q, canonical for canonical v: one more exact product (R^-1 = ex N mod q is not stored;
+      // v N^-1 R^-1 = y ex N^-1 ... use the stored exit constant on the pre-scale value instead)
+      v = sp.f.mulmod(sp.finish_d(x[i]), F.exd);
+      v = v < 0.0 ? __dadd_rn(v, sp.f.q) : v;
+      v = v >= sp.f.q ? __dadd_rn(v, -sp.f.q) : v;
+      if constexpr (EPI >= TB_EPI_EXIT_SIGNED) v = (v <= (double)((i64)F.q >> 1)) ? v : __dadd_rn(v, -sp.f.q);
+    }
+    r[i] = v;
+  }
+  if (tb_block_any(bad | (minhi < band_hi))) {
+    if (threadIdx.x == 0) todo[tile_flag_index()] = 1;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) d[(long)tb::tile_x(tr, i, f0) << c.LB] = tb::FastF64Pol::to_int(r[i]);
 }
 
 // =====================================================================================
