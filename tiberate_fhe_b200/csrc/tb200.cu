@@ -334,6 +334,7 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.qinv = 1.0 / (double)qi;
       f.exd = f.ex > qi / 2 ? -(double)(qi - f.ex) : (double)f.ex;
       f.Rcd = Rm > qi / 2 ? -(double)(qi - Rm) : (double)Rm;
+      f.c96 = (u64)(((unsigned __int128)1 << 96) % qi);
       {
         u64 pp = 1 % qi;
         for (int kk = 0; kk < K; ++kk) pp = h_mulmod(pp, (u64)q[no + kk] % qi, qi);

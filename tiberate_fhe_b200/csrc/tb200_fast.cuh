@@ -33,6 +33,7 @@ struct __align__(16) TbFastPrime {
   double qd, qinv;   // q and 1/q as doubles
   double exd, nid;   // ex and N^-1 mod q, centred into (-q/2, q/2]
   double Rcd, cPd;   // R mod q and P mod q (P = product of the special primes) centred
+  u64 c96;           // 2^96 mod q (tb_montred_wide)
 };
 
 namespace tb {

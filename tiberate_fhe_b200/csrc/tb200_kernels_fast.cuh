@@ -71,6 +71,10 @@ __device__ __forceinline__ i64 fast_prologue(const TbFwdAArgs& a, const TbFastPr
   }
 }
 
+// bound (in units of 4q) of the lazy 60-bit extension sum before term k is added: 1 after the first term, +1 per
+// term, back to 1 by a reduction whenever it has reached 4
+__host__ __device__ constexpr int ext_terms(int k) { return k <= 4 ? k : (k - 5) % 3 + 2; }
+
 // ModUp extend for the 16 residues of a thread, ALPHA digits each: loads first, then the Shoup sums.
 template <int ALPHA>
 __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& a, const TbFastPrime& P,
@@ -103,12 +107,20 @@ __device__ __forceinline__ void extend_prologue(i64 (&x)[16], const TbFwdAArgs& 
 #pragma unroll
         for (int k = 1; k < ALPHA; ++k) v += tb::shoup_lazy((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
       } else {
-        v = tb::shoup((u64)(d[i][0] + (i64)P.off), C[0], Cs[0], P.q);
+        // 60-bit limbs (q < 2^60): lazy quotients as well -- every term below 4q, so a sum of four stays below
+        // 16q < 2^64; a longer sum is brought below 4q before the term that would overflow (ext_terms: the
+        // bound in units of 4q).  Pass A takes any U below 8q.
+        const u64 q4 = P.q2 + P.q2, q8 = q4 + q4;
+        v = tb::shoup_lazy((u64)(d[i][0] + (i64)P.off), C[0], Cs[0], P.q);
 #pragma unroll
         for (int k = 1; k < ALPHA; ++k) {
-          v += tb::shoup((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
-          v = (v >= P.q2) ? v - P.q2 : v;
+          if (ext_terms(k) == 4) {
+            v = (v >= q8) ? v - q8 : v;
+            v = (v >= q4) ? v - q4 : v;
+          }
+          v += tb::shoup_lazy((u64)(d[i][k] + (i64)P.off), C[k], Cs[k], P.q);
         }
+        if (ext_terms(ALPHA) > 2) v = (v >= q8) ? v - q8 : v;
       }
       x[h + i] = (i64)v;
     }
@@ -495,6 +507,15 @@ __device__ __forceinline__ i64 tb_montred128(__int128 T, u64 q4, u64 k) {
   return (i64)(((u64)hi << 2) | (lo >> 62)) + (i64)t + ((lo & TB_MASK62) != 0 ? 1 : 0);
 }
 
+// Montgomery reduction of any signed 128-bit T (|T| < 2^127), result in [0, 2q): the bits above 2^96 are folded
+// first, T = th 2^96 + tl  ->  tl + th (2^96 mod q), |.| < 2^97, so the reduced value lies in (-2^35, 2^35 + q].
+__device__ __forceinline__ i64 tb_montred_wide(__int128 T, const TbPrime& P, u64 c96) {
+  const i64 th = (i64)(T >> 96);
+  const __int128 tl = T - ((__int128)th << 96);  // [0, 2^96)
+  i64 r = tb_montred128(tl + (__int128)th * (i64)c96, P.q4, P.k) + P.q2;
+  return r >= P.q2 ? r - P.q2 : r;
+}
+
 // x in (-2q, 4q) -> [0, 2q)   (key residues may be negative: mont_sub keeps negatives)
 __device__ __forceinline__ i64 tb_norm2q(i64 x, i64 q2) {
   x = (x >= q2) ? x - q2 : x;
@@ -638,21 +659,29 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
     o1.x = tb_montred128(a1x, P.q4, P.k) + P.q;
     o1.y = tb_montred128(a1y, P.q4, P.k) + P.q;
   } else {
-    i64 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    // 60-bit limbs: extension residues in [0, 2q) (< 2^61) times key residues (|k| < 2^62): |term| < 2^123, the sum
+    // over <= 16 groups fits 128 bits; one reduction per sum (tb_montred_wide) instead of one Montgomery product
+    // and one normalisation per term.
+    __int128 a0x = 0, a0y = 0, a1x = 0, a1y = 0;
+    const i64* ep = ext + (((long)bt * ng) * rowsE + t) * N + sj;
+    const long estride = (long)rowsE * N, koff = (long)(level + t) * key.rs + j;
+#pragma unroll 2
     for (int gi = 0; gi < ng; ++gi) {
       const int gid = lv->g[gi].gid;
-      const longlong2 e = ldext(ext + (((long)bt * ng + gi) * rowsE + t) * N + sj);
-      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + (long)(level + t) * key.rs + j);
-      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + (long)(level + t) * key.rs + j);
-      a0x = tb_norm2q(a0x + tb_mm_ss(e.x, kb.x, P.q4, P.k), P.q2);
-      a0y = tb_norm2q(a0y + tb_mm_ss(e.y, kb.y, P.q4, P.k), P.q2);
-      a1x = tb_norm2q(a1x + tb_mm_ss(e.x, ka.x, P.q4, P.k), P.q2);
-      a1y = tb_norm2q(a1y + tb_mm_ss(e.y, ka.y, P.q4, P.k), P.q2);
+      const longlong2 e = ldext(ep);
+      const longlong2 kb = *reinterpret_cast<const longlong2*>(key.b[gid] + koff);
+      const longlong2 ka = *reinterpret_cast<const longlong2*>(key.a[gid] + koff);
+      ep += estride;
+      a0x += (__int128)e.x * kb.x;
+      a0y += (__int128)e.y * kb.y;
+      a1x += (__int128)e.x * ka.x;
+      a1y += (__int128)e.y * ka.y;
     }
-    o0.x = a0x;
-    o0.y = a0y;
-    o1.x = a1x;
-    o1.y = a1y;
+    const u64 c96 = f.fp[level + t].c96;
+    o0.x = tb_montred_wide(a0x, P, c96);
+    o0.y = tb_montred_wide(a0y, P, c96);
+    o1.x = tb_montred_wide(a1x, P, c96);
+    o1.y = tb_montred_wide(a1y, P, c96);
   }
   if (has_add) {
     o0.x += add0x;
