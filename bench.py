@@ -37,6 +37,16 @@ def preset():
     return PRESETS[LOGN]["q"], PRESETS[LOGN]["K"]
 
 
+def fp64_peak(roof, clocks):
+    """Completes roofline.fp64_issue with the peak at the SM clock sampled during the run."""
+    f = roof.get("fp64_issue") if roof else None
+    if f:
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        f["peak"] = f["peak_lanes_per_clk_per_sm"] * 148 * mhz * 1e6 / 1e12
+        f["frac"] = f["achieved"] / f["peak"]
+    return roof
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -326,6 +336,21 @@ def run_ours(args):
         nl, tms = kern[top]
         roof = {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src, "avg_launch_ms": tms / nl}
+    if roof and top == "k_fast_fwd_A":
+        # The resource that actually binds this kernel class: FP64 instruction issue.  Algorithmic FP64 lane-instructions
+        # per HMult: a pass-A butterfly is 8 (one error-free modular product + 2 adds) = 4 per residue
+        # and stage; the rescale-enter prologue adds 1 conversion, the ModUp extend 1 conversion per digit and 7 per
+        # digit product.  Peak: 62 FP64 lane-instructions / clk / SM measured (profiles/r02_ubench_fp64.txt) x 148 SMs
+        # x the SM clock sampled during the run.
+        LA_ = LOGN - 8
+        nF = ctx.narrow_rows(1, L)                       # FP64 (scale-prime) rows among the L ordinary limbs
+        S_ = int(ctx.ks_state_info(1)[0])                # digit rows = sum of the group sizes
+        per_row_ext = 8 * (S_ - ng) + (1 + 4 * LA_) * ng - (8 * (K - 1) + 1 + 4 * LA_)   # own group's pair is skipped
+        fp64_per_op = N * (4 * nF * (1 + 4 * LA_) + nF * per_row_ext)
+        nl, tms = kern[top]
+        roof["fp64_issue"] = {"lane_instructions_per_op": fp64_per_op,
+                              "achieved": fp64_per_op * B * psteps / (tms / 1e3) / 1e12,
+                              "peak_lanes_per_clk_per_sm": 62.0, "unit": "T FP64 lane-instructions/s"}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if roof and os.path.exists(tpath):
         with open(tpath) as f:
@@ -350,8 +375,11 @@ def run_ours(args):
     dout = [[out0[k * sb:(k + 1) * sb], out1[k * sb:(k + 1) * sb]] for k in range(2)]  # two output slots
     s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
+    # slot events persist across steps: consecutive steps run back to back without a host synchronisation, so the first
+    # sub-batches of a step must wait for the last users of their device slots in the previous step
+    ev_cmp, ev_out = [None, None], [None, None]
+
     def e2e_step(compute=True):
-        ev_cmp, ev_out = [None, None], [None, None]
         for i in range(nsub):
             k = i % 2
             with torch.cuda.stream(s_in):
@@ -421,14 +449,15 @@ def run_ours(args):
     dp_in = [[torch.empty(sb, nar_in, PRB, dtype=torch.uint8, device=dev) for _ in range(4)] for _ in range(2)]
     dp_out = [[torch.empty(sb, nar_out, PRB, dtype=torch.uint8, device=dev) for _ in range(2)] for _ in range(2)]
 
+    ev_cmp_p, ev_out_p = [None, None], [None, None]  # fresh slot events for the packed pipeline (same rule as above)
+
     def e2e_packed_step(compute=True):
-        ev_cmp, ev_out = [None, None], [None, None]
         for i in range(nsub):
             k = i % 2
             sl = slice(i * sb, (i + 1) * sb)
             with torch.cuda.stream(s_in):
-                if ev_cmp[k] is not None:
-                    s_in.wait_event(ev_cmp[k])
+                if ev_cmp_p[k] is not None:
+                    s_in.wait_event(ev_cmp_p[k])
                 for d, dp, hp, hw in zip(din[k], dp_in[k], hp_in, hw_in):
                     dp.copy_(hp[sl], non_blocking=True)
                     d[:, nar_in:].copy_(hw[sl], non_blocking=True)
@@ -436,23 +465,23 @@ def run_ours(args):
                 ev_in.record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)
-                if ev_out[k] is not None:
-                    s_cmp.wait_event(ev_out[k])
+                if ev_out_p[k] is not None:
+                    s_cmp.wait_event(ev_out_p[k])
                 if compute:
                     for d, dp in zip(din[k], dp_in[k]):
                         ctx.unpack41(dp, d[:, :nar_in], 0)
                     ctx.cc_mult_relin(0, din[k][0], din[k][1], din[k][2], din[k][3], evk, dout[k][0], dout[k][1], True)
                     for d, dp in zip(dout[k], dp_out[k]):
                         ctx.pack41(d[:, :nar_out], dp, 1)
-                ev_cmp[k] = torch.cuda.Event()
-                ev_cmp[k].record(s_cmp)
+                ev_cmp_p[k] = torch.cuda.Event()
+                ev_cmp_p[k].record(s_cmp)
             with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_cmp[k])
+                s_out.wait_event(ev_cmp_p[k])
                 for hp, hw, d, dp in zip(hp_out, hw_out, dout[k], dp_out[k]):
                     hp[sl].copy_(dp, non_blocking=True)
                     hw[sl].copy_(d[:, nar_out:], non_blocking=True)
-                ev_out[k] = torch.cuda.Event()
-                ev_out[k].record(s_out)
+                ev_out_p[k] = torch.cuda.Event()
+                ev_out_p[k].record(s_out)
 
     e2e_int64_step = e2e_step
     e2e_step = e2e_packed_step  # noqa: F811  (e2e_timed calls the name)
@@ -531,7 +560,7 @@ def run_ours(args):
                                    "cc_mult(pre_rescale)+relinearize", "batch_per_gpu": B, "chunk": args.chunk,
                        "sharding": "ciphertext batch, no data-path collective",
                        "l2": "inputs (>= 17 GiB per step at batch 256) exceed the 126 MB L2"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": fp64_peak(roof, clocks),
             "cpu_baseline": cpu, "reference_cuda_ext": ref_ext, "kernel_time_share": shares, "kernel_us_per_op": kernel_us_per_op,
             "hmult_hbm_roofline": {"algorithmic_bytes_per_op": alg_bytes, "roofline_ops_per_s": peak * 1e9 / alg_bytes,
                                    "frac": value / world / (peak * 1e9 / alg_bytes),

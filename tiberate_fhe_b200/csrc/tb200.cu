@@ -381,12 +381,16 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
     cP[(size_t)P + g] = (i64)h_mulmod(pp, (u64)(Rbig % qq), qq);
   }
   // ModDown in product form: B_k = prod_{j<=k} P_j^-1 mod q_g
-  std::vector<u64> bn((size_t)(K + 1) * P * 2, 0);
+  // rows [0, K): (-B_k, Shoup); row K: (B_{K-1}, Shoup); rows K+1+k: (P_k^-1, Shoup) for the composed form
+  std::vector<u64> bn((size_t)(2 * K + 1) * P * 2, 0);
   for (int g = 0; g < no; ++g) {
     const u64 qq = (u64)q[g];
     u64 B = 1;
     for (int kk = 0; kk < K; ++kk) {
-      B = h_mulmod(B, h_invmod_prime((u64)q[no + kk] % qq, qq), qq);
+      const u64 pinv = h_invmod_prime((u64)q[no + kk] % qq, qq);
+      bn[((size_t)(K + 1 + kk) * P + g) * 2] = pinv;
+      bn[((size_t)(K + 1 + kk) * P + g) * 2 + 1] = h_shoup(pinv, qq);
+      B = h_mulmod(B, pinv, qq);
       const u64 neg = (qq - B) % qq;
       bn[((size_t)kk * P + g) * 2] = neg;
       bn[((size_t)kk * P + g) * 2 + 1] = h_shoup(neg, qq);
@@ -1339,8 +1343,8 @@ static size_t ks_ws_elems(const tb200_ctx* c, int level) {
 static int ks_digits(tb200_ctx* c, int level, int nb, TbView a, TbView state, tb200_stream st) {
   const TbKsLevel& lv = c->ks[level];
   if (lv.nown > 0)
-    LAUNCH(k_digits, dim3((unsigned)((c->N + 255) / 256), (unsigned)lv.nown, (unsigned)nb), dim3(256), st, c->dev(),
-           c->d_ks + level, a, state, c->N);
+    LAUNCH(k_digits, dim3((unsigned)((c->N / 2 + 255) / 256), (unsigned)lv.nown, (unsigned)nb),
+           dim3(c->N / 2 < 256 ? c->N / 2 : 256), st, c->dev(), c->d_ks + level, a, state, c->N);
   return 0;
 }
 

@@ -733,36 +733,71 @@ struct TbKsLevel {
   TbKsGroup g[TB_MAXG];
 };
 
-// ModUp digits (pre_extend, ckks_engine.py:889-921): one thread per (coefficient, group).
+// ModUp digits (pre_extend, ckks_engine.py:889-921): one thread per (coefficient pair, group).
 // a: [L][N] canonical coefficient domain; state: [L][N] (digit rows, same row numbering).
-__global__ void __launch_bounds__(256) k_digits(TbDev c, const TbKsLevel* lv, TbView a, TbView st, int N) {
-  const TbKsGroup& G = lv->g[lv->own[blockIdx.y]];
-  const int bt = blockIdx.z;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
+// W residues per thread (W = 2: 128-bit accesses), A = compile-time bound on the group size: the A source limbs
+// are loaded before the dependent chain of Montgomery products starts.
+template <int A, int W>
+__device__ __forceinline__ void digits_body(const TbDev& c, const TbKsGroup& G, const TbView& a, const TbView& st, int bt,
+                                            int j) {
   const int alpha = G.alpha;
-  i64 s[TB_MAXA];
-  const i64 a0 = a.row(bt, G.src_row0)[j];
+  i64 in[A][W], s[A][W];
 #pragma unroll
-  for (int i = 0; i < TB_MAXA; ++i) s[i] = a0;
+  for (int i = 0; i < A; ++i)
+    if (i < alpha) {
+      if constexpr (W == 2) {
+        const longlong2 v = *reinterpret_cast<const longlong2*>(a.row(bt, G.src_row0 + i) + j);
+        in[i][0] = v.x;
+        in[i][1] = v.y;
+      } else {
+        in[i][0] = a.row(bt, G.src_row0 + i)[j];
+      }
+    }
 #pragma unroll
-  for (int i = 0; i < TB_MAXA - 1; ++i) {
+  for (int i = 0; i < A; ++i)
+#pragma unroll
+    for (int w = 0; w < W; ++w) s[i][w] = in[0][w];
+#pragma unroll
+  for (int i = 0; i < A - 1; ++i) {
     if (i + 1 < alpha) {
       const TbPrime& P1 = c.pr[G.src_prime0 + i + 1];
-      const i64 Y = tb_mm_ss(a.row(bt, G.src_row0 + i + 1)[j] - s[i + 1], G.Y[i], P1.q4, P1.k);
-      s[i + 1] = Y;
+      i64 Y[W];
 #pragma unroll
-      for (int jj = i + 2; jj < TB_MAXA; ++jj) {
+      for (int w = 0; w < W; ++w) s[i + 1][w] = Y[w] = tb_mm_ss(in[i + 1][w] - s[i + 1][w], G.Y[i], P1.q4, P1.k);
+#pragma unroll
+      for (int jj = i + 2; jj < A; ++jj) {
         if (jj < alpha) {
           const TbPrime& Pj = c.pr[G.src_prime0 + jj];
-          s[jj] += tb_mm_ss(Y, G.Lsc[i][jj], Pj.q4, Pj.k);
+#pragma unroll
+          for (int w = 0; w < W; ++w) s[jj][w] += tb_mm_ss(Y[w], G.Lsc[i][jj], Pj.q4, Pj.k);
         }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < TB_MAXA; ++i)
-    if (i < alpha) st.row(bt, G.state_row0 + i)[j] = s[i];
+  for (int i = 0; i < A; ++i)
+    if (i < alpha) {
+      if constexpr (W == 2) {
+        longlong2 o;
+        o.x = s[i][0];
+        o.y = s[i][1];
+        *reinterpret_cast<longlong2*>(st.row(bt, G.state_row0 + i) + j) = o;
+      } else {
+        st.row(bt, G.state_row0 + i)[j] = s[i][0];
+      }
+    }
+}
+__global__ void __launch_bounds__(256) k_digits(TbDev c, const TbKsLevel* lv, TbView a, TbView st, int N) {
+  const TbKsGroup& G = lv->g[lv->own[blockIdx.y]];
+  const int bt = blockIdx.z;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (j >= N) return;
+  if (G.alpha <= 4) {  // CTA-uniform
+    digits_body<4, 2>(c, G, a, st, bt, j);
+  } else {
+    digits_body<TB_MAXA, 1>(c, G, a, st, bt, j);
+    digits_body<TB_MAXA, 1>(c, G, a, st, bt, j + 1);
+  }
 }
 
 // ModUp extend for every group of the level (he_fused_cuda.cu:298-311):

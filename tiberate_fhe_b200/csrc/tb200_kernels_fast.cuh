@@ -702,8 +702,8 @@ __global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const Tb
 // ModDown, mod q (he_fused_cuda.cu:471-519 composes x <- (x - p_k) P_k^-1 for k = K-1..0; expanded:
 // x = c B_{K-1} - sum_k p_k B_k with B_k = prod_{j<=k} P_j^-1).  The special limbs p_k are the exact
 // integers produced by the chain-backward step (representative-sensitive, kept exact); the result is
-// canonical, hence identical to the reference's.  bn: [(K+1)][P][2] = (-B_k mod q, Shoup) for k < K,
-// then (B_{K-1}, Shoup).  TAIL as in k_divide_by_p.
+// canonical, hence identical to the reference's.  bn: [(2K+1)][P][2] = (-B_k mod q, Shoup) for k < K,
+// then (B_{K-1}, Shoup), then (P_k^-1 mod q, Shoup) for k < K.  TAIL as in k_divide_by_p.
 template <int TAIL>
 __global__ void __launch_bounds__(256) k_fast_divide_by_p(TbDevFast f, TbView cc, TbView p, TbView add, TbView out,
                                                           const u64* bn, int K, int prime0, int N) {
@@ -717,16 +717,30 @@ __global__ void __launch_bounds__(256) k_fast_divide_by_p(TbDevFast f, TbView cc
   const u64* bk = b + 2 * (long)K * f.P;
   i64 y0, y1;
   if (P.small) {
-    // 40-bit limbs: lazy Shoup quotients (every term below 4q), no reduction between the K + 1 terms
-    // (sum < 4 (K + 1) q < 2^46), one exact reduction at the end on the FP64 pipe
-    u64 x0 = tb::shoup_lazy((u64)(cv.x + (i64)P.q), bk[0], bk[1], P.q);
-    u64 x1 = tb::shoup_lazy((u64)(cv.y + (i64)P.q), bk[0], bk[1], P.q);
-    for (int k = 0; k < K; ++k) {
-      const longlong2 pv = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
-      const u64* bb = b + 2 * (long)k * f.P;
-      x0 += tb::shoup_lazy((u64)(pv.x + (i64)P.off), bb[0], bb[1], P.q);
-      x1 += tb::shoup_lazy((u64)(pv.y + (i64)P.off), bb[0], bb[1], P.q);
+    // 40-bit limbs: the reference's own composition x <- (x - p_k) P_k^-1, k = K-1 .. 0, with lazy Shoup quotients:
+    // K products instead of the K + 1 of the expanded form; every intermediate is below 4q, `2 off - p_k` is a
+    // non-negative representative of -p_k (off: multiple of q in [2^61, 2^62), |p_k| < 2^62); one exact reduction
+    // at the end on the FP64 pipe.  The (first four) special limbs are loaded before the chain starts.
+    longlong2 pv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < K) pv[k] = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
+    const u64* pi = b + 2 * (long)(K + 1) * f.P;  // rows K+1 .. 2K: (P_k^-1 mod q, Shoup)
+    u64 x0 = (u64)(cv.x + (i64)P.q), x1 = (u64)(cv.y + (i64)P.q);
+    const u64 off2 = P.off << 1;
+    for (int k = K - 1; k >= 4; --k) {  // more than four special primes: the upper ones straight from memory
+      const longlong2 pk = *reinterpret_cast<const longlong2*>(p.row(bt, k) + j);
+      const u64* bb = pi + 2 * (long)k * f.P;
+      x0 = tb::shoup_lazy(x0 + (off2 - (u64)pk.x), bb[0], bb[1], P.q);
+      x1 = tb::shoup_lazy(x1 + (off2 - (u64)pk.y), bb[0], bb[1], P.q);
     }
+#pragma unroll
+    for (int k = 3; k >= 0; --k)
+      if (k < K) {
+        const u64* bb = pi + 2 * (long)k * f.P;
+        x0 = tb::shoup_lazy(x0 + (off2 - (u64)pv[k].x), bb[0], bb[1], P.q);
+        x1 = tb::shoup_lazy(x1 + (off2 - (u64)pv[k].y), bb[0], bb[1], P.q);
+      }
     const tb::FastF64Pol pol{P.qd, P.qinv};
     double r0 = pol.reduce(tb::FastF64Pol::from_int((i64)x0)), r1 = pol.reduce(tb::FastF64Pol::from_int((i64)x1));
     r0 = r0 < 0.0 ? __dadd_rn(r0, pol.q) : r0;
