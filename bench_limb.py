@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 
 def run(rank: int, world: int, local: int, steps: int = 10, warmup: int = 3, batch: int = 8, level: int = 0,
-        logN: int = 17, overlap: bool = True, slices: int = 2) -> dict | None:
+        logN: int = 17, overlap: bool = True, slices: int = 1, shard_special: bool = True) -> dict | None:
     import torch
     import torch.distributed as dist
 
@@ -87,22 +87,56 @@ def run(rank: int, world: int, local: int, steps: int = 10, warmup: int = 3, bat
     key = KeySwitchKeyView([(b[ids].contiguous(), a_[ids].contiguous()) for b, a_ in key_full], N)
     a_loc = a[:, rows].contiguous()
     o0l, o1l = torch.empty_like(a_loc), torch.empty_like(a_loc)
-    ks = LimbShardedKeySwitch(ctx, overlap=overlap)
+    ks = LimbShardedKeySwitch(ctx, overlap=overlap, shard_special=shard_special)
 
     nsl = max(1, min(slices, batch))
     cuts = [(i * batch // nsl, (i + 1) * batch // nsl) for i in range(nsl)]
 
-    def step():  # `slices` batched key switches in flight: the collectives of the later ones run under the earlier kernels
-        started = [ks.start(level, a_loc[lo:hi], slot=i) for i, (lo, hi) in enumerate(cuts)]
-        for (lo, hi), st in zip(cuts, started):
-            ks.finish(level, st, key, o0l[lo:hi], o1l[lo:hi])
+    # The batch is a stream of `slices` batched key switches.  Software pipeline of depth one, across step boundaries:
+    # the digits + all-gather of the NEXT slice are issued (tb200_ks_digits + ncclAllGather, on their two alternating
+    # state slots) before the current slice is finished, so the collective travels under the current slice's kernels.
+    pend = {"st": None, "k": 0}
+
+    def step(last=True):  # last: nothing follows (drain): every started key switch is finished inside the call
+        for i, (lo, hi) in enumerate(cuts):
+            if pend["st"] is None:
+                pend["st"] = ks.start(level, a_loc[lo:hi], slot=pend["k"] % 2)
+            cur = pend["st"]
+            pend["st"] = None
+            nxt = None
+            if not (last and i == nsl - 1):
+                nlo, nhi = cuts[(i + 1) % nsl]
+
+                def nxt(nlo=nlo, nhi=nhi):
+                    pend["st"] = ks.start(level, a_loc[nlo:nhi], slot=(pend["k"] + 1) % 2)
+
+            ks.finish(level, cur, key, o0l[lo:hi], o1l[lo:hi], between=nxt)
+            pend["k"] += 1
+
+    def timed_stream():
+        for i in range(warmup):
+            step(last=i == warmup - 1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(last=i == steps - 1)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps
 
     step()
     torch.cuda.synchronize()
     ok = bool(torch.equal(o0l, r0[:, rows]) and torch.equal(o1l, r1[:, rows]))
+    o0l.zero_()
+    o1l.zero_()
+    step(last=False)  # and through the pipelined path: two steps, the second one drains
+    step(last=True)
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(o0l, r0[:, rows]) and torch.equal(o1l, r1[:, rows]))
     flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    ms = timed(step)
+    ms = timed_stream()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
@@ -112,15 +146,19 @@ def run(rank: int, world: int, local: int, steps: int = 10, warmup: int = 3, bat
     S = ctx.ks_state_info(level)[0]
     out = None
     if rank == 0:
-        ideal = (L + K) / (-(-L // world) + K)  # the special limbs are replicated on every rank
+        # limb count only (a special limb costs ~2.5 scale limbs, so the replicated flow sits below its figure)
+        sp_mode = "their key sums sharded too (second all-gather of 2 K N words per polynomial)" if ks.shard_special \
+            else "special limbs replicated"
+        ideal = (L + K) / (-(-L // world) + (-(-K // world) if ks.shard_special else K))
         out = {"metric": f"key-switch ops/s at logN={logN}, limb-sharded", "value": batch / (ms / 1e3), "unit": "ops/s",
                "n_gpus": world, "ms_per_step": ms, "batch": batch, "scaling": "strong",
                "one_gpu_ops_per_s": batch / (ms_one / 1e3), "speedup_vs_one_gpu": ms_one / ms,
                "ideal_speedup": ideal, "bit_exact_vs_unsharded": bool(int(flag.item())), "overlap": overlap, "slices": nsl,
-               "allgather_bytes_per_keyswitch": S * N * 8,
+               "shard_special": bool(ks.shard_special),
+               "allgather_bytes_per_keyswitch": S * N * 8 + (2 * ctx.ks_sp_info()[0] * N * 8 if ks.shard_special else 0),
                "config": {"workload": f"logN{logN} preset, level {level}: {L} ordinary + {K} special limbs, {ng} digit "
                                       f"groups; {batch} polynomials key switched per step, limbs dealt to {world} ranks by "
-                                      f"digit group, special limbs replicated (ideal speed-up {ideal:.2f})",
+                                      f"digit group, {sp_mode} (limb-count ideal {ideal:.2f})",
                           "local_limbs_rank0": len(rows)}}
     if not bool(int(flag.item())):
         raise SystemExit("limb-sharded key switch differs from the unsharded one")
@@ -141,7 +179,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--slices", type=int, default=2)
+    ap.add_argument("--slices", type=int, default=1)
+    ap.add_argument("--replicate-special", action="store_true", help="the reference's flow: special limbs on every rank")
     args, _ = ap.parse_known_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -149,7 +188,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    out = run(rank, world, local, args.steps, args.warmup, args.batch, args.level, overlap=not args.no_overlap, slices=args.slices)
+    out = run(rank, world, local, args.steps, args.warmup, args.batch, args.level, overlap=not args.no_overlap, slices=args.slices,
+              shard_special=not args.replicate_special)
     if rank == 0:
         out.update({"steps": args.steps, "warmup": args.warmup, "dtype": "int64", "data": "synthetic",
                     "higher_is_better": True})

@@ -211,12 +211,31 @@ int tb200_ks_finish(tb200_ctx*, int level, int batch, const tb200_poly* state, c
                     int tail, tb200_stream);
 /* tb200_ks_finish in two calls, so that the ModUp of the digit groups this rank owns runs while the all-gather
  * of the other ranks' digits is still in flight (tiberate_fhe_b200/dist.py): tb200_ks_modup(which = 1 own /
- * 2 foreign / 0 all) extends + forward-transforms (pass A) the selected groups into the context workspace,
+ * 2 foreign / 0 all; + 4: see tb200_ks_core_sp) extends + forward-transforms (pass A) the selected groups into the context workspace,
  * tb200_ks_core does the rest.  batch <= chunk (the extended limbs live in the workspace between the calls). */
 int tb200_ks_modup(tb200_ctx*, int level, int batch, const tb200_poly* state, int which, tb200_stream);
 int tb200_ks_core(tb200_ctx*, int level, int batch, const tb200_poly* state, const tb200_ksk* ksk,
                   const tb200_poly* add0, const tb200_poly* add1, const tb200_poly* out0, const tb200_poly* out1,
                   int tail, tb200_stream);
+/* Limb-sharded key switch with the special limbs sharded as well.  tb200_ks_finish / tb200_ks_core replicate the
+ * K special limbs on every rank, as the reference does (tiberate/context/rns_partition.py:34-52: every device
+ * holds the special group; ckks_engine.py:1365-1400 extends and multiplies all of them per device).  Here a rank
+ * computes the key sums of ITS SHARE of the special limbs only (ceil(K / world) limbs per rank, rank order), and one
+ * more all-gather of 2 K N words per polynomial -- issued by the caller while the ordinary limbs are processed --
+ * completes them before ModDown:
+ *   tb200_ks_modup(which + 4)  extend + pass A of the local ordinary rows and of the share of the special rows
+ *   tb200_ks_core_sp           pass B, key inner product, inverse transform of the share -> the rank's segment of sp
+ *   (all-gather of the segments)
+ *   tb200_ks_core_ord          the same for the local ordinary rows (the sums stay in the context workspace)
+ *   tb200_ks_moddown           chain-backward on the complete special limbs, ModDown, tail (as tb200_ks_finish)
+ * sp: dense int64 [rows][batch][2][N] (special limb, polynomial, key half) with rows = world * ceil(K / world);
+ * tb200_ks_sp_info: out[0] = rows, out[1] = rows per segment, out[2], out[3] = [s0, s1) the special limbs of this rank.
+ * batch <= chunk.  The outputs are the same bits as tb200_ks_finish. */
+int tb200_ks_sp_info(const tb200_ctx*, int32_t* out);
+int tb200_ks_core_sp(tb200_ctx*, int level, int batch, const tb200_ksk* ksk, int64_t* sp, tb200_stream);
+int tb200_ks_core_ord(tb200_ctx*, int level, int batch, const tb200_ksk* ksk, tb200_stream);
+int tb200_ks_moddown(tb200_ctx*, int level, int batch, int64_t* sp, const tb200_poly* add0, const tb200_poly* add1,
+                     const tb200_poly* out0, const tb200_poly* out1, int tail, tb200_stream);
 /* cc_mult (+relinearize) :1640-1732.  a*, b*: [L_in][N] at `level`; with pre_rescale the product
  * lives at level+1 and has L_in-1 rows.  out0/out1 canonical coefficient domain. */
 int tb200_cc_mult_relin(tb200_ctx*, int level, int batch, const tb200_poly* a0, const tb200_poly* a1,

@@ -92,14 +92,18 @@ def _sharded_ks_worker(rank, world, port, seed):
         key = KeySwitchKeyView([None if p is None else (torch.from_numpy(np.ascontiguousarray(p[0][ids])),
                                                         torch.from_numpy(np.ascontiguousarray(p[1][ids]))) for p in evk],
                                octx.N)
-        for level in (0, 2, 4):  # at level 4 rank 1 owns no ordinary limb any more
+        assert ks.shard_special  # default flow: the special limbs' key sums are sharded too (second all-gather)
+        ks_repl = LimbShardedKeySwitch(ctx, shard_special=False)  # the reference's replicated special limbs
+        for level in (0, 2, 4):  # at level 4 rank 1 owns no ordinary limb any more (both fall back to replication)
             a = eng.uniform(rng, octx.level_primes(level, False))
             want0, want1 = eng.create_switcher(a, evk, level)
             a_loc = shard_rows(torch.from_numpy(a), ctx, level)
-            o0, o1 = torch.zeros_like(a_loc), torch.zeros_like(a_loc)
-            ks(level, a_loc, key, o0, o1)
             rows = [g - level for g in ctx.local_rows(level)]
-            assert np.array_equal(o0.numpy(), want0[rows]) and np.array_equal(o1.numpy(), want1[rows]), (rank, level)
+            for k_ in (ks, ks_repl):
+                o0, o1 = torch.zeros_like(a_loc), torch.zeros_like(a_loc)
+                k_(level, a_loc, key, o0, o1)
+                assert np.array_equal(o0.numpy(), want0[rows]) and np.array_equal(o1.numpy(), want1[rows]), \
+                    (rank, level, k_.shard_special)
         # batched: [B, L_local, N] through one all-gather (state stored [rows, B, N])
         ctx.set_chunk(3)
         for level in (0, 2):
@@ -160,5 +164,5 @@ def _sharded_ks_worker(rank, world, port, seed):
         dist.destroy_process_group()
 
 
-def test_limb_sharded_keyswitch_two_ranks_gloo():
+def test_limb_sharded_keyswitch_two_ranks_gloo(emu_lib):  # the fixture (re)builds tests/emu before the ranks start
     mp.spawn(_sharded_ks_worker, args=(2, _free_port(), 5), nprocs=2, join=True)

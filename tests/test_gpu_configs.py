@@ -130,6 +130,33 @@ def test_logN17_limb_sharded_keyswitch_vs_oracle(h, world):
                 sw0[rows] = h.host(o0)
             assert np.array_equal(got0, want0) and np.array_equal(got1, want1), f"world {world} level {level}"
             assert np.array_equal(sw0, want_sw[0]), f"switch_key tail, world {world} level {level}"
+            # the same with the key sums of the special limbs sharded as well (tb200_ks_core_sp): every rank, also one
+            # that has run out of ordinary limbs, computes its share; the second all-gather is emulated by copies
+            sps = []
+            for c, key, st in zip(ctxs, keys, states):
+                rows_sp, seg_sp, s0, s1 = c.ks_sp_info()
+                sp = torch.zeros(rows_sp, 1, 2, N, dtype=torch.int64, device=st.device)
+                c.ks_modup(level, st, which=0 + 4)
+                c.ks_core_sp(level, 1, key, sp)
+                sps.append((sp, c.rank * seg_sp, seg_sp))
+            torch.cuda.synchronize()
+            for r, (spr, r0, sg) in enumerate(sps):
+                for sp, _, _ in sps:
+                    if sp is not spr:
+                        sp[r0:r0 + sg].copy_(spr[r0:r0 + sg])
+            got0, got1, sw0 = np.zeros_like(want0), np.zeros_like(want1), np.zeros_like(want0)
+            for c, key, st, (_, _, rows), (sp, _, _) in zip(ctxs, keys, states, infos, sps):
+                if not rows:
+                    continue
+                o0, o1 = h.zeros(len(rows), N), h.zeros(len(rows), N)
+                c.ks_core_ord(level, 1, key, o0)
+                sp2 = sp.clone()  # chain-backward rewrites the special limbs in place
+                c.ks_moddown(level, sp, o0, o1)
+                got0[rows], got1[rows] = h.host(o0), h.host(o1)
+                c.ks_moddown(level, sp2, o0, o1, add0=h.dev(add[rows]), tail=2)
+                sw0[rows] = h.host(o0)
+            assert np.array_equal(got0, want0) and np.array_equal(got1, want1), f"sharded special, world {world} level {level}"
+            assert np.array_equal(sw0, want_sw[0]), f"sharded special, switch_key tail, world {world} level {level}"
     finally:
         for c in ctxs:
             c.close()

@@ -71,6 +71,10 @@ SIGNATURES = {
     "tb200_unpack41": (_i, [_vp, _i, _i, _i, _vp, C.c_int64, C.c_int64, PP, _vp]),
     "tb200_pack41": (_i, [_vp, _i, _i, _i, PP, _vp, C.c_int64, C.c_int64, _vp]),
     "tb200_ks_core": (_i, [_vp, _i, _i, PP, C.POINTER(Ksk), PP, PP, PP, PP, _i, _vp]),
+    "tb200_ks_sp_info": (_i, [_vp, _vp]),
+    "tb200_ks_core_sp": (_i, [_vp, _i, _i, C.POINTER(Ksk), _vp, _vp]),
+    "tb200_ks_core_ord": (_i, [_vp, _i, _i, C.POINTER(Ksk), _vp]),
+    "tb200_ks_moddown": (_i, [_vp, _i, _i, _vp, PP, PP, PP, PP, _i, _vp]),
     "tb200_cc_mult_relin": (_i, [_vp, _i, _i, PP, PP, PP, PP, C.POINTER(Ksk), PP, PP, _i, _vp]),
     "tb200_cc_mult_triplet": (_i, [_vp, _i, _i, PP, PP, PP, PP, PP, PP, PP, _i, _vp]),
     "tb200_relinearize": (_i, [_vp, _i, _i, PP, PP, PP, C.POINTER(Ksk), PP, PP, _vp]),

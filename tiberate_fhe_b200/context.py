@@ -397,6 +397,39 @@ class Tb200Context:
                                     _stream(out0))
         self.lib.check(rc, "ks_core")
 
+    # ---- the same with the special limbs sharded too (include/tb200.h: tb200_ks_core_sp) -------
+    def ks_sp_info(self):
+        """(rows of the sp buffer, rows per rank segment, s0, s1): this rank computes special limbs [s0, s1)."""
+        out = (C.c_int32 * 4)()
+        self.lib.check(self.lib.tb200_ks_sp_info(self.h, out), "ks_sp_info")
+        return tuple(out)
+
+    def _sp_check(self, what, sp, batch):
+        rows = self.ks_sp_info()[0]
+        want = [batch * 2 * self.N, 2 * self.N, self.N, 1]
+        if tuple(sp.shape) != (rows, batch, 2, self.N) or not _is_int64(sp) or _strides(sp) != want:
+            raise Tb200Error(f"{what}: sp must be a contiguous int64 tensor [{rows}, {batch}, 2, {self.N}]")
+
+    def ks_core_sp(self, level: int, batch: int, ksk: KeySwitchKeyView, sp):
+        """Key sums of this rank's share of the special limbs (after ks_modup(which + 4)) -> its segment of sp."""
+        self._sp_check("ks_core_sp", sp, batch)
+        rc = self.lib.tb200_ks_core_sp(self.h, level, int(batch), C.byref(ksk.c), C.c_void_p(_ptr(sp)), _stream(sp))
+        self.lib.check(rc, "ks_core_sp")
+
+    def ks_core_ord(self, level: int, batch: int, ksk: KeySwitchKeyView, like):
+        """Key sums of the local ordinary limbs (they stay in the context workspace until ks_moddown)."""
+        rc = self.lib.tb200_ks_core_ord(self.h, level, int(batch), C.byref(ksk.c), _stream(like))
+        self.lib.check(rc, "ks_core_ord")
+
+    def ks_moddown(self, level: int, sp, out0, out1, add0=None, add1=None, tail: int = 0):
+        r = self._rows(level)
+        self._shapes("ks_moddown", level, ("out0", out0, r), ("out1", out1, r), ("add0", add0, r), ("add1", add1, r))
+        batch = self._batch(out0)
+        self._sp_check("ks_moddown", sp, batch)
+        rc = self.lib.tb200_ks_moddown(self.h, level, batch, C.c_void_p(_ptr(sp)), self._pp(add0), self._pp(add1),
+                                       self._pp(out0), self._pp(out1), int(tail), _stream(out0))
+        self.lib.check(rc, "ks_moddown")
+
     def cc_mult_relin(self, level: int, a0, a1, b0, b1, evk: KeySwitchKeyView, out0, out1, pre_rescale: bool = True):
         r = self._rows(level)
         ro = r - (1 if pre_rescale else 0)

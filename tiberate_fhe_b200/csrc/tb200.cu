@@ -1363,7 +1363,16 @@ static int ks_core_rows(const tb200_ctx* c, int p0, int E) { return (c->fast && 
 // ModUp of the selected digit groups (sel: 0 every group, 1 the groups this rank owns, 2 the other ranks' groups):
 // digits -> extended limbs, with forward pass A fused in on the mod-q path.  Splitting by ownership lets a limb-
 // sharded key switch extend its own groups while the all-gather of the others is in flight (dist.py).
-static int ks_modup(tb200_ctx* c, int level, int nb, TbView state, i64* ws, tb200_stream st, bool own_prefilled, int sel) {
+// This rank's share [s0, s1) of the K special limbs when their key sums are sharded as well (tb200_ks_core_sp):
+// equal segments of ceil(K / world) limbs in rank order, the last ones possibly short or empty.
+static void sp_share(const tb200_ctx* c, int* s0, int* s1, int* seg) {
+  const int sg = (c->K + c->world - 1) / c->world;
+  *seg = sg;
+  *s0 = c->rank * sg < c->K ? c->rank * sg : c->K;
+  *s1 = (c->rank + 1) * sg < c->K ? (c->rank + 1) * sg : c->K;
+}
+static int ks_modup(tb200_ctx* c, int level, int nb, TbView state, i64* ws, tb200_stream st, bool own_prefilled, int sel,
+                    bool sp_own_only = false) {
   const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
   const TbKsLevel& lv = c->ks[level];
   const int ng = lv.ngroups;
@@ -1390,6 +1399,18 @@ static int ks_modup(tb200_ctx* c, int level, int nb, TbView state, i64* ws, tb20
   fa.skip_own = own_prefilled ? 1 : 0;
   fa.sel = sel;
   fa.nsel = nsel;
+  if (sp_own_only) {  // the ordinary rows, then only this rank's share of the special rows
+    int s0, s1, seg;
+    sp_share(c, &s0, &s1, &seg);
+    if (L > 0 && (rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fa, L, nb * nsel, st))) return rc;
+    if (s1 > s0) {
+      TbFwdAArgs fb = fa;
+      fb.prime0 += L + s0;
+      fb.dst = rows_from(fb.dst, L + s0);
+      if ((rc = launch_fast_fwd_A<TB_FPRO_EXTEND>(c, fb, s1 - s0, nb * nsel, st))) return rc;
+    }
+    return 0;
+  }
   const int nf = ks_core_rows(c, p0, E);
   const bool split_a = c->LB == 8 && ntt_lw(c) == 12 - c->LA && nf > 0;  // FP64-only pass A instantiation exists
   if (split_a) {
@@ -1573,12 +1594,15 @@ extern "C" int tb200_ks_finish(tb200_ctx* c, int level, int batch, const tb200_p
 extern "C" int tb200_ks_modup(tb200_ctx* c, int level, int batch, const tb200_poly* state, int which, tb200_stream st) {
   int rc = check_level(c, level, batch);
   if (rc) return rc;
-  if (which < 0 || which > 2) return fail(TB200_EINVAL, "ks_modup: which must be 0 (all), 1 (own) or 2 (foreign)");
+  const bool sp_own_only = (which & 4) != 0;  // + 4: of the special rows only this rank's share (tb200_ks_core_sp)
+  which &= ~4;
+  if (which < 0 || which > 2) return fail(TB200_EINVAL, "ks_modup: which must be 0 (all), 1 (own) or 2 (foreign), + 4");
+  if (sp_own_only && !c->fast) return fail(TB200_EINVAL, "ks_modup: the special-limb share needs the mod-q path");
   if (batch > c->chunk) return fail(TB200_EINVAL, "ks_modup: batch %d exceeds the chunk %d", batch, c->chunk);
   CHECK_POLY(state);
   SET_DEVICE(c->device);
   if ((rc = ws_reserve(c, ks_ws_elems(c, level) * (size_t)batch))) return rc;
-  if ((rc = ks_modup(c, level, batch, view(state), c->ws, st, false, which))) return rc;
+  if ((rc = ks_modup(c, level, batch, view(state), c->ws, st, false, which, sp_own_only))) return rc;
   POST();
   return 0;
 }
@@ -1601,6 +1625,141 @@ extern "C" int tb200_ks_core(tb200_ctx* c, int level, int batch, const tb200_pol
   rc = ks_finish(c, level, batch, view(state), key, view(add0 ? add0 : out0), view(add1 ? add1 : out1), view(out0),
                  view(out1), tail, c->ws, st, nullptr, true);
   if (rc) return rc;
+  POST();
+  return 0;
+}
+
+// ---- limb-sharded key switch with the special limbs sharded as well ---------------------------------------------
+// tb200_ks_finish / tb200_ks_core replicate the K special limbs: every rank extends, transforms and multiplies all of
+// them (the reference does the same, rns_partition.py:34-52).  They are 60-bit limbs (2.5x the cost of a scale limb),
+// so at logN17 (73 + 6 limbs) they cap the speed-up at 1.66x / 2.5x on 2 / 4 GPUs.  Here every rank computes the key
+// sums of its share of them only and ONE more all-gather (2 K N words per polynomial, issued by the caller while the
+// ordinary limbs are still being processed) completes them before ModDown:
+//   tb200_ks_modup(which | 4)   extend + pass A of the ordinary rows and of the rank's share of the special rows
+//   tb200_ks_core_sp            pass B + key inner product + inverse transform of that share -> its segment of `sp`
+//   -- all-gather of the segments (asynchronous) --
+//   tb200_ks_core_ord           the same for the local ordinary rows (sums stay in the context workspace)
+//   tb200_ks_moddown            chain-backward on the complete special limbs + ModDown + tail
+// sp: dense [world * ceil(K / world)][batch][2][N] (special limb, polynomial, key half); rank r owns rows
+// [r seg, (r + 1) seg).  Results are the same bits as tb200_ks_finish (every step is the same arithmetic).
+static int ks_sums(tb200_ctx* c, int level, int nb, const TbKskDev& key, i64* ws, int part, i64* sp, tb200_stream st) {
+  const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K;
+  const TbKsLevel& lv = c->ks[level];
+  const int ng = lv.ngroups;
+  const TbKsLevel* dlv = c->d_ks + level;
+  i64* ext = ws;
+  i64* acc = ext + (size_t)nb * ng * E * N;
+  int s0, s1, seg, rc = 0;
+  sp_share(c, &s0, &s1, &seg);
+  const int r0 = part == 0 ? 0 : L + s0, r1 = part == 0 ? L : L + s1;
+  if (r1 <= r0) return 0;
+  int nf = part == 0 ? ks_core_rows(c, p0, E) : 0;  // leading rows of the range that go through the fused FP64 core
+  if (nf > L) nf = L;
+  if (nf > 0) {
+    TbKsCoreArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.lv = dlv;
+    ka.key = key;
+    ka.ext = ext;
+    ka.acc = acc;
+    ka.p0 = p0;
+    ka.N = N;
+    ka.rowsE = E;
+    ka.nb = nb;
+    ka.pr = c->d_primes;
+    if ((rc = launch_ks_core(c, ka, nf, st))) return rc;
+  }
+  const int i0 = r0 > nf ? r0 : nf;
+  if (i0 < r1) {
+    const TbView er = rows_from(dense(ext, E, N), i0);
+    if ((rc = launch_fast_B(c, false, er, er, r1 - i0, nb * ng, p0 + i0, st, 0, nullptr, 1))) return rc;
+    LAUNCH(k_fast_mac, dim3((unsigned)(((N / 2 + 255) / 256) * nb), (unsigned)(r1 - i0), 1u),
+           dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), c->devf(), dlv, key, (const i64*)ext, acc, p0, N, E, nb,
+           (const i64*)nullptr, (const i64*)nullptr, (const i64*)c->d_cP, i0, 0u);
+    const TbView ar = rows_from(dense(acc, E, N), i0);
+    if ((rc = launch_fast_B(c, true, ar, ar, r1 - i0, nb * 2, p0 + i0, st, TB_INV_IN_DOUBLE))) return rc;
+  }
+  // inverse pass A' + exit; the special share goes straight to its segment of sp ([k][polynomial][half][N])
+  const TbView src = rows_from(dense(acc, E, N), r0);
+  TbView dst = src;
+  if (part == 1) {
+    dst.p = sp + (size_t)s0 * nb * 2 * N;
+    dst.bs = N;
+    dst.rs = (long)nb * 2 * N;
+  }
+  return launch_fast_inv_A(c, src, dst, r1 - r0, nb * 2, p0 + r0, 1, st);
+}
+static int ks_sp_check(tb200_ctx* c, int level, int batch, const char* what) {
+  int rc = check_level(c, level, batch);
+  if (rc) return rc;
+  if (!c->fast) return fail(TB200_EINVAL, "%s: needs the mod-q path (tb200_ctx_set_fast)", what);
+  if (batch > c->chunk) return fail(TB200_EINVAL, "%s: batch %d exceeds the chunk %d", what, batch, c->chunk);
+  if (c->ws_elems < ks_ws_elems(c, level) * (size_t)batch) return fail(TB200_EINVAL, "%s: call tb200_ks_modup first", what);
+  return 0;
+}
+extern "C" int tb200_ks_sp_info(const tb200_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(TB200_EINVAL, "ks_sp_info: null argument");
+  int s0, s1, seg;
+  sp_share(c, &s0, &s1, &seg);
+  out[0] = seg * c->world;  // rows of the sp buffer
+  out[1] = seg;             // rows per rank segment (segment r starts at row r * seg)
+  out[2] = s0;
+  out[3] = s1;
+  return 0;
+}
+extern "C" int tb200_ks_core_sp(tb200_ctx* c, int level, int batch, const tb200_ksk* ksk, int64_t* sp, tb200_stream st) {
+  int rc = ks_sp_check(c, level, batch, "ks_core_sp");
+  if (rc) return rc;
+  if (!sp || ((uintptr_t)sp & 15)) return fail(TB200_EINVAL, "ks_core_sp: sp must be a 16-byte aligned device pointer");
+  TbKskDev key;
+  if ((rc = make_key(c, level, ksk, &key))) return rc;
+  SET_DEVICE(c->device);
+  if ((rc = ks_sums(c, level, batch, key, c->ws, 1, sp, st))) return rc;
+  POST();
+  return 0;
+}
+extern "C" int tb200_ks_core_ord(tb200_ctx* c, int level, int batch, const tb200_ksk* ksk, tb200_stream st) {
+  int rc = ks_sp_check(c, level, batch, "ks_core_ord");
+  if (rc) return rc;
+  TbKskDev key;
+  if ((rc = make_key(c, level, ksk, &key))) return rc;
+  SET_DEVICE(c->device);
+  if ((rc = ks_sums(c, level, batch, key, c->ws, 0, nullptr, st))) return rc;
+  POST();
+  return 0;
+}
+extern "C" int tb200_ks_moddown(tb200_ctx* c, int level, int batch, int64_t* sp, const tb200_poly* add0,
+                                const tb200_poly* add1, const tb200_poly* out0, const tb200_poly* out1, int tail,
+                                tb200_stream st) {
+  int rc = ks_sp_check(c, level, batch, "ks_moddown");
+  if (rc) return rc;
+  if (tail < 0 || tail > 2) return fail(TB200_EINVAL, "ks_moddown: tail must be 0, 1 or 2");
+  if (!sp || ((uintptr_t)sp & 15)) return fail(TB200_EINVAL, "ks_moddown: sp must be a 16-byte aligned device pointer");
+  CHECK_POLY(out0);
+  CHECK_POLY(out1);
+  if (tail != 0) CHECK_POLY(add0);
+  if (tail == 1) CHECK_POLY(add1);
+  SET_DEVICE(c->device);
+  const int N = c->N, p0 = c->lstart[level], L = c->num_ord - p0, E = L + c->K, ng = c->ks[level].ngroups;
+  if (L < 1) {  // a rank without ordinary limbs at this level only contributed its special share
+    POST();
+    return 0;
+  }
+  i64* acc = c->ws + (size_t)batch * ng * E * N;
+  for (int h = 0; h < 2; ++h) {
+    TbView cc;
+    cc.p = acc + (size_t)h * E * N;
+    cc.bs = 2L * E * N;
+    cc.rs = N;
+    TbView p;
+    p.p = sp + (size_t)h * N;
+    p.bs = 2L * N;
+    p.rs = (long)batch * 2 * N;
+    const int t = (tail == 2 && h == 1) ? 0 : tail;
+    const tb200_poly* add = h == 0 ? add0 : add1;
+    const tb200_poly* out = h == 0 ? out0 : out1;
+    if ((rc = moddown(c, level, batch, cc, p, view(add ? add : out), view(out), t, st))) return rc;
+  }
   POST();
   return 0;
 }

@@ -81,7 +81,7 @@ class LimbShardedKeySwitch:
     while it is in flight; the other groups' ModUp (which=2) and the core (tb200_ks_core) follow once the
     digits have arrived.  overlap=False: gather, then tb200_ks_finish."""
 
-    def __init__(self, ctx, group=None, overlap: bool = True):
+    def __init__(self, ctx, group=None, overlap: bool = True, shard_special: bool = True):
         import torch.distributed as dist
 
         self.ctx, self.group, self.overlap = ctx, group, overlap
@@ -89,6 +89,31 @@ class LimbShardedKeySwitch:
         if ctx.world != self.world or ctx.rank != dist.get_rank(group):
             raise ValueError("context rank/world must match the process group")
         self._state = {}
+        # shard_special (needs overlap=True and the mod-q path): the key sums of the K special limbs are sharded too --
+        # every rank extends / transforms / multiplies only its share of them (they are 60-bit limbs, 2.5x the cost
+        # of a scale limb, and replicated they cap the speed-up at ~1.7x / 2.5x on 2 / 4 GPUs), and a second, small
+        # all-gather (2 K N words per polynomial) completes them before ModDown while the ordinary limbs are still
+        # being processed.  Same bits as the replicated flow (include/tb200.h: tb200_ks_core_sp).
+        self.shard_special = bool(shard_special and overlap and self.world > 1)
+        self._sp = {}
+
+    def _levels_all_ranks_busy(self, level: int) -> bool:
+        """True when every rank still owns an ordinary limb at `level` (the sharded-special flow assumes it; deep
+        levels where a rank has run out of limbs use the replicated flow -- decided by rule, the same on every rank)."""
+        ctx = self.ctx
+        owners = {prime_owner(ctx, p) for p in range(level, ctx.P_global - ctx.K)}
+        return len(owners) == self.world
+
+    def _sp_buffer(self, batch, like, slot):
+        import torch
+
+        rows, seg, _, _ = self.ctx.ks_sp_info()
+        key = (batch, like.device, slot)
+        sp = self._sp.get(key)
+        if sp is None:
+            sp = torch.zeros((rows, batch, 2, self.ctx.N), dtype=torch.int64, device=like.device)
+            self._sp[key] = sp
+        return sp, seg
 
     def _state_buffer(self, level, like, slot=0):
         """Digit-state buffer, stored [state_rows, (batch,) N]: the rows of one owner are contiguous for the whole
@@ -118,17 +143,42 @@ class LimbShardedKeySwitch:
         if self.world > 1:  # every rank takes part, also those that own nothing at this level
             views = [store[r * seg:(r + 1) * seg] for r in range(self.world)]
             work = dist.all_gather(views, store[row0:row0 + seg], group=self.group, async_op=self.overlap)
-        return state, (work if self.overlap else None)
+        return state, (work if self.overlap else None), slot
 
-    def finish(self, level: int, started, ksk_local, out0, out1, add0=None, add1=None, tail: int = 0):
+    def finish(self, level: int, started, ksk_local, out0, out1, add0=None, add1=None, tail: int = 0, between=None):
+        """between: optional callable that starts the NEXT key switch of a stream (`start(...)` on another slot).
+        It is invoked where its collective cannot delay this one: collectives of one communicator run in issue
+        order, so the next key switch's (large) digit all-gather must be issued after this one's special-limb
+        all-gather, not before."""
         ctx = self.ctx
-        state, work = started
+        state, work, slot = started
+        sharded_sp = self.shard_special and self._levels_all_ranks_busy(level)
+        if between is not None and not sharded_sp:
+            between()
         if out0.shape[-2] == 0:
             if work is not None:
                 work.wait()
             return out0, out1
         if not self.overlap:
             ctx.ks_finish(level, state, ksk_local, out0, out1, add0=add0, add1=add1, tail=tail)
+            return out0, out1
+        if sharded_sp:
+            import torch.distributed as dist
+
+            batch = out0.shape[0] if out0.dim() == 3 else 1
+            sp, seg = self._sp_buffer(batch, out0, slot)
+            ctx.ks_modup(level, state, which=1 + 4)
+            if work is not None:
+                work.wait()
+            ctx.ks_modup(level, state, which=2 + 4)
+            ctx.ks_core_sp(level, batch, ksk_local, sp)  # this rank's share of the special limbs first ...
+            views = [sp[r * seg:(r + 1) * seg] for r in range(self.world)]
+            work2 = dist.all_gather(views, sp[ctx.rank * seg:(ctx.rank + 1) * seg], group=self.group, async_op=True)
+            if between is not None:
+                between()
+            ctx.ks_core_ord(level, batch, ksk_local, out0)  # ... the ordinary limbs while those sums travel
+            work2.wait()
+            ctx.ks_moddown(level, sp, out0, out1, add0=add0, add1=add1, tail=tail)
             return out0, out1
         ctx.ks_modup(level, state, which=1)  # own groups: their digits never left this GPU
         if work is not None:
