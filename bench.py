@@ -583,7 +583,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="ciphertext pairs per GPU per step")
-    ap.add_argument("--chunk", type=int, default=32, help="ciphertexts per internal pass (workspace size)")
+    ap.add_argument("--chunk", type=int, default=64, help="ciphertexts per internal pass (workspace size: 0.38 GB each)")
     ap.add_argument("--e2e-batch", type=int, default=64)
     ap.add_argument("--e2e-sub", type=int, default=8, help="sub-batch of the end-to-end pipeline")
     ap.add_argument("--no-reference-ext", action="store_true")

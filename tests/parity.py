@@ -78,6 +78,24 @@ class Setup:
         self.ctx.close()
 
 
+def far_primes(logN: int, num_scales: int, K: int) -> list[int]:
+    """A toy chain whose 55-bit scale primes and 60-bit base / special primes lie FAR from a power of two
+    (0.7 * 2^55, 0.75 * 2^60), unlike every prime of the reference's presets and of toy_primes: bounds of the
+    lazy butterflies, offsets and reductions that only hold near 2^b would show here."""
+    from oracle.context import is_prime
+
+    def below(bound, count, skip=()):
+        out, c = [], bound // (2 << logN)
+        while len(out) < count:
+            q = c * (2 << logN) + 1
+            if q not in skip and is_prime(q):
+                out.append(q)
+            c -= 1
+        return out
+
+    return below(7 * (1 << 55) // 10, num_scales) + below(3 << 58, 1 + K)
+
+
 def eq(h: Harness, got, want, what: str):
     g = h.host(got)
     w = np.asarray(want)

@@ -85,6 +85,17 @@ def test_engine_wide_scale_primes(h):
         s.close()
 
 
+def test_engine_primes_far_from_a_power_of_two(h):
+    """Primes at 0.7 * 2^55 / 0.75 * 2^60: nothing may rely on q being just below a power of two."""
+    s = Setup(h, 8, parity.far_primes(8, 4, 2), 2, seed=13)
+    try:
+        parity.check_ntt(s, level=0, with_special=True, batch=1)
+        for level in (0, 3):
+            parity.check_engine(s, level, ops=("keyswitch", "rotate", "cc_mult", "pc_mult"))
+    finally:
+        s.close()
+
+
 def test_engine_batched_and_chunked(h):
     s = Setup.toy(h, 8, 4, 2, seed=7)
     try:

@@ -56,6 +56,21 @@ def test_toy_rings(h, logN, ns, K):
         s.close()
 
 
+@pytest.mark.parametrize("logN", [9, 12])
+def test_primes_far_from_a_power_of_two(h, logN):
+    """Every prime of the reference lies just below a power of two; this chain (0.7 * 2^55 scale primes,
+    0.75 * 2^60 base / special primes) checks that no bound of the lazy arithmetic relies on that."""
+    s = Setup(h, logN, parity.far_primes(logN, 4, 2), 2, seed=500 + logN)
+    try:
+        parity.check_ntt(s, 0, True, 2)
+        for level in (0, 2, 4):
+            for mode in parity.ENGINE_MODES:
+                parity.set_mode(s, mode)
+                parity.check_engine(s, level)
+    finally:
+        s.close()
+
+
 def _preset(h, logN, **kw):
     from oracle.context import PRESETS
 

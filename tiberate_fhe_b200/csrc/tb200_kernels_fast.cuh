@@ -540,7 +540,7 @@ __device__ __forceinline__ unsigned tb_ntt_slot_perm(unsigned i, unsigned g, int
 }
 
 // galois != 0 (hoisted rotations): the extension limbs are read through the NTT-domain automorphism above.
-__global__ void __launch_bounds__(256) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
+__global__ void __launch_bounds__(256, 4) k_fast_mac(TbDev c, TbDevFast f, const TbKsLevel* lv, TbKskDev key,
                                                   const i64* ext, i64* acc, int level, int N, int rowsE, int nb,
                                                   const i64* nadd0, const i64* nadd1, const i64* cP, int row0,
                                                   unsigned galois) {
