@@ -90,9 +90,10 @@ int tb200_ctx_set_f64_share(tb200_ctx*, int eighths);
 /* Mod-q path only: scheduling knobs for A/B measurements; results are bit-identical for every setting.
  *   TB200_TUNE_FUSED_CORE (default 1): FP64 limbs run pass B of every digit group, the key inner product
  *     and inverse pass B as one kernel (no HBM round trip of the transformed extensions); 0: three kernels.
- *   TB200_TUNE_SIDE_ROWS (default 0: measured no gain, the first kernel fills the GPU): inside a key switch
- *     the launches over the 60-bit limb rows (integer pipes) are forked onto a library-owned stream and
- *     joined again, beside the launches over the FP64 limb rows; 0: one stream.
+ *   TB200_TUNE_SIDE_ROWS (bit mask): the launches over the 60-bit limb rows (integer pipes) are forked onto a
+ *     library-owned stream and joined again, beside the launches over the FP64 limb rows.  Bit 0: inside a key
+ *     switch (measured no gain: the first kernel fills the GPU); bit 1: the input transforms of cc_mult, whose
+ *     60-bit launches are a third of a wave each; 0: one stream.
  *   TB200_TUNE_FUSED_MODDOWN (default 0: measured 63 us against 36 + 20 us separately, B200 logN16): ModDown and the relinearisation / switch-key tail run inside the
  *     exit of inverse pass A of the ordinary limbs (after the special limbs were transformed and
  *     chain-reduced); 0: separate kernels over the coefficient-domain sums.

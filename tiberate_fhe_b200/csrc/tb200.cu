@@ -570,7 +570,7 @@ extern "C" int tb200_ctx_set_tuning(tb200_ctx* c, int knob, int value) {
       c->fused_core = value != 0;
       return 0;
     case TB200_TUNE_SIDE_ROWS:
-      c->side_rows = value != 0;
+      c->side_rows = value;  // bit 0: key-switch rows, bit 1: the 60-bit rows of the input transforms of cc_mult
       return 0;
     case TB200_TUNE_FUSED_MODDOWN:
       c->fused_moddown = value != 0;
@@ -1133,8 +1133,10 @@ static int launch_ks_core(const tb200_ctx* c, const TbKsCoreArgs& a, int rows, t
   return 0;
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
+// st_int: stream of the launches over the non-FP64 rows (default: st); they only depend on each other
 static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
-                              int rescale_level, tb200_stream st) {
+                              int rescale_level, tb200_stream st, tb200_stream st_int = nullptr) {
+  if (!st_int) st_int = st;
   TbFwdAArgs a;
   memset(&a, 0, sizeof(a));
   a.src = src;
@@ -1157,7 +1159,7 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
         b.dst = rows_from(b.dst, nf);
         b.resc += 3 * (size_t)nf;
         b.row_shift = nf;
-        if ((rc = launch_fast_fwd_A_rows<TB_FPRO_RESCALE_ENTER, false>(c, b, rows - nf, batch, st))) return rc;
+        if ((rc = launch_fast_fwd_A_rows<TB_FPRO_RESCALE_ENTER, false>(c, b, rows - nf, batch, st_int))) return rc;
       }
     } else if ((rc = launch_fast_fwd_A<TB_FPRO_RESCALE_ENTER>(c, a, rows, batch, st))) {
       return rc;
@@ -1169,9 +1171,15 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
       b.prime0 += nf;
       b.dst = rows_from(b.dst, nf);
       b.row_shift = nf;
-      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_ENTER, false>(c, b, rows - nf, batch, st))) return rc;
+      if ((rc = launch_fast_fwd_A_rows<TB_FPRO_ENTER, false>(c, b, rows - nf, batch, st_int))) return rc;
     }
   } else if ((rc = launch_fast_fwd_A<TB_FPRO_ENTER>(c, a, rows, batch, st))) {
+    return rc;
+  }
+  if (st_int != st && nf > 0) {  // pass B split by hand: FP64 rows on st, the rest on st_int
+    if ((rc = launch_fast_B_rows(c, false, true, dst, dst, nf, batch, prime0, st))) return rc;
+    if (nf < rows)
+      rc = launch_fast_B_rows(c, false, false, rows_from(dst, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st_int);
     return rc;
   }
   return launch_fast_B(c, false, dst, dst, rows, batch, prime0, st);
@@ -1446,7 +1454,7 @@ static int ks_finish(tb200_ctx* c, int level, int nb, TbView state, const TbKskD
     // (optionally on a forked stream: they load the integer pipes, the FP64 rows the FP64 pipe).
     const int nf = ks_core_rows(c, p0, E);
     tb200_stream sst = st;
-    if (nf > 0 && nf < E && c->side_rows && !g_prof_on) {
+    if (nf > 0 && nf < E && (c->side_rows & 1) && !g_prof_on) {
       if ((rc = side_stream_fork(c, st))) return rc;
       sst = (tb200_stream)c->side;
     }
@@ -1943,10 +1951,18 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
   // four rescale + forward transforms suffice and the tensor product reads them twice
   const bool square = a0.p == b0.p && a1.p == b1.p && a0.bs == b0.bs && a1.bs == b1.bs && a0.rs == b0.rs &&
                       a1.rs == b1.rs;
+  // TB200_TUNE_SIDE_ROWS bit 1: the 60-bit rows of the input transforms (a third of a wave per launch) run on the
+  // forked side stream under the FP64 rows' launches
+  tb200_stream sst = st;
+  if (fast && (c->side_rows & 2) && !g_prof_on) {
+    int rc = side_stream_fork(c, st);
+    if (rc) return rc;
+    sst = (tb200_stream)c->side;
+  }
   for (int i = 0; i < (square ? 2 : 4); ++i) {
     TbView xi = dense(x + i * pe, L, N);
     if (fast) {
-      int rc = fast_forward_enter(c, in[i], xi, L, nb, lvl, pre_rescale ? level : -1, st);
+      int rc = fast_forward_enter(c, in[i], xi, L, nb, lvl, pre_rescale ? level : -1, st, sst);
       if (rc) return rc;
     } else if (pre_rescale) {
       rescale_impl(c, level, nb, in[i], xi, 1, st);
@@ -1956,6 +1972,10 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
       int rc = ntt_forward(c, in[i], xi, L, nb, lvl, true, st);
       if (rc) return rc;
     }
+  }
+  if (sst != st) {
+    int rc = side_stream_join(c, st);
+    if (rc) return rc;
   }
   LAUNCH(k_tensor, grid_pw(c, L, nb, 2), dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), dense(x, L, N),
          dense(x + pe, L, N), dense(x + (square ? 0 : 2) * pe, L, N), dense(x + (square ? 1 : 3) * pe, L, N), d0, d1,
