@@ -202,6 +202,52 @@ def test_limb_sharded_keyswitch_matches_single_device(h, world):
                 sw0[rows] = o0
             assert np.array_equal(got0, want0) and np.array_equal(got1, want1), f"level {level}"
             assert np.array_equal(sw0, want_sw[0]), f"switch_key tail, level {level}"
+            # the same with the key sums of the special limbs sharded too (tb200_ks_core_sp / _ord / tb200_ks_moddown):
+            # every rank -- also one without ordinary limbs left -- computes its share (world 3, K = 2: one rank has
+            # none), the second all-gather is emulated by copies
+            keys = []
+            for c in ctxs:
+                ids = c.local_prime_ids
+                keys.append(KeySwitchKeyView([None if p is None else (np.ascontiguousarray(p[0][ids]),
+                                                                      np.ascontiguousarray(p[1][ids])) for p in evk], N))
+            sps = []
+            for c, st, key in zip(ctxs, states, keys):
+                rows_sp, seg_sp, s0, s1 = c.ks_sp_info()
+                assert rows_sp == seg_sp * world and 0 <= s0 <= s1 <= K
+                sp = np.zeros((rows_sp, 1, 2, N), dtype=np.int64)
+                c.ks_modup(level, st, which=0 + 4)
+                c.ks_core_sp(level, 1, key, sp)
+                sps.append((sp, c.rank * seg_sp, seg_sp))
+            for spr, r0, sg in sps:
+                for sp, _, _ in sps:
+                    if sp is not spr:
+                        sp[r0:r0 + sg] = spr[r0:r0 + sg]
+            got0, got1, sw0 = np.zeros_like(want0), np.zeros_like(want1), np.zeros_like(want0)
+            for c, key, (_, _, rows), (sp, _, _) in zip(ctxs, keys, infos, sps):
+                if not rows:
+                    continue
+                o0 = np.zeros((len(rows), N), dtype=np.int64)
+                o1 = np.zeros_like(o0)
+                c.ks_core_ord(level, 1, key, o0)
+                sp2 = sp.copy()  # chain-backward rewrites the special limbs in place
+                c.ks_moddown(level, sp, o0, o1)
+                got0[rows], got1[rows] = o0, o1
+                c.ks_moddown(level, sp2, o0, o1, add0=np.ascontiguousarray(add[rows]), tail=2)
+                sw0[rows] = o0
+            assert np.array_equal(got0, want0) and np.array_equal(got1, want1), f"sharded special, level {level}"
+            assert np.array_equal(sw0, want_sw[0]), f"sharded special, switch_key tail, level {level}"
+        # argument checks of the new entries: wrong sp shape; batch beyond the chunk
+        from tiberate_fhe_b200 import Tb200Error
+
+        c0 = ctxs[0]
+        rows0 = len(c0.local_rows(0))
+        with pytest.raises(Tb200Error, match="sp must be"):
+            c0.ks_core_sp(0, 1, keys[0], np.zeros((1, 1, 2, N), dtype=np.int64)[:, :, :1])
+        with pytest.raises(Tb200Error):
+            c0.set_chunk(1)
+            big = np.zeros((c0.ks_sp_info()[0], 2, 2, N), dtype=np.int64)
+            c0.ks_core_sp(0, 2, keys[0], big)  # batch 2 > chunk 1
+        _ = rows0
     finally:
         for c in ctxs:
             c.close()
