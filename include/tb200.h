@@ -100,11 +100,13 @@ int tb200_ctx_set_f64_share(tb200_ctx*, int eighths);
  *   TB200_TUNE_STREAM_WS (default 1): the scratch of an engine call is leased from the device's stream-ordered
  *     memory pool on the caller's stream (see "Streams, threads and CUDA graphs" below); 0: one grow-only
  *     workspace per context (single stream, growth synchronises the device).
+ *   TB200_TUNE_FUSED_TENSOR (default 1): in cc_mult the forward pass B of the last operand and the tensor product
+ *     run as one kernel on the FP64 limbs (the transformed operand never goes to HBM); 0: separate kernels.
  *   TB200_TUNE_SUM_NTT (default 1): tb200_ntt runs the deferred-reduction kernels (the reference's lazy
  *     representatives from one reduction modulo 2q per pass) on tiles of 40-bit limbs whose inputs are lazy
  *     values in [0, 2q), the generic exact kernels on the rest; 0: generic kernels only. */
 enum tb200_tuning { TB200_TUNE_FUSED_CORE = 0, TB200_TUNE_SIDE_ROWS = 1, TB200_TUNE_FUSED_MODDOWN = 2,
-                    TB200_TUNE_STREAM_WS = 3, TB200_TUNE_SUM_NTT = 4 };
+                    TB200_TUNE_STREAM_WS = 3, TB200_TUNE_SUM_NTT = 4, TB200_TUNE_FUSED_TENSOR = 5 };
 int tb200_ctx_set_tuning(tb200_ctx*, int knob, int value);
 
 /* ---- packed wire format ------------------------------------------------------------------------------

@@ -176,7 +176,7 @@ class Tb200Context:
         """Share (0..8 eighths) of the small-prime limbs transformed on the FP64 pipe (mod-q path)."""
         self.lib.check(self.lib.tb200_ctx_set_f64_share(self.h, int(eighths)), "set_f64_share")
 
-    TUNE_FUSED_CORE, TUNE_SIDE_ROWS, TUNE_FUSED_MODDOWN, TUNE_STREAM_WS, TUNE_SUM_NTT = 0, 1, 2, 3, 4
+    TUNE_FUSED_CORE, TUNE_SIDE_ROWS, TUNE_FUSED_MODDOWN, TUNE_STREAM_WS, TUNE_SUM_NTT, TUNE_FUSED_TENSOR = 0, 1, 2, 3, 4, 5
 
     def set_tuning(self, knob: int, value: int):
         """Scheduling knobs of the mod-q path (include/tb200.h: enum tb200_tuning); results never change."""

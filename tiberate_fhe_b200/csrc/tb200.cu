@@ -336,6 +336,10 @@ static tb200_ctx* ctx_create_impl(int device, int logN, int Pg, int num_special,
       f.Rcd = Rm > qi / 2 ? -(double)(qi - Rm) : (double)Rm;
       f.c96 = (u64)(((unsigned __int128)1 << 96) % qi);
       {
+        const u64 ri = h_invmod_prime(Rm, qi);
+        f.Rid = ri > qi / 2 ? -(double)(qi - ri) : (double)ri;
+      }
+      {
         u64 pp = 1 % qi;
         for (int kk = 0; kk < K; ++kk) pp = h_mulmod(pp, (u64)q[no + kk] % qi, qi);
         f.cPd = pp > qi / 2 ? -(double)(qi - pp) : (double)pp;
@@ -580,6 +584,9 @@ extern "C" int tb200_ctx_set_tuning(tb200_ctx* c, int knob, int value) {
       return 0;
     case TB200_TUNE_SUM_NTT:
       c->sum_ntt = value != 0;
+      return 0;
+    case TB200_TUNE_FUSED_TENSOR:
+      c->fused_tensor = value != 0;
       return 0;
   }
   return fail(TB200_EINVAL, "unknown tuning knob %d", knob);
@@ -1134,9 +1141,13 @@ static int launch_ks_core(const tb200_ctx* c, const TbKsCoreArgs& a, int rows, t
 }
 // forward transform with the "enter" (x R) or "rescale + enter" prologue, mod q; dst dense or strided
 // st_int: stream of the launches over the non-FP64 rows (default: st); they only depend on each other
+// skip_b_f64 (out, optional): pass B of the leading FP64 rows is left to the caller (k_fast_fwd_B_tensor); receives
+// their count (0: nothing was skipped)
 static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int rows, int batch, int prime0,
-                              int rescale_level, tb200_stream st, tb200_stream st_int = nullptr) {
+                              int rescale_level, tb200_stream st, tb200_stream st_int = nullptr,
+                              int* skip_b_f64 = nullptr) {
   if (!st_int) st_int = st;
+  if (skip_b_f64) *skip_b_f64 = 0;
   TbFwdAArgs a;
   memset(&a, 0, sizeof(a));
   a.src = src;
@@ -1175,6 +1186,12 @@ static int fast_forward_enter(const tb200_ctx* c, TbView src, TbView dst, int ro
     }
   } else if ((rc = launch_fast_fwd_A<TB_FPRO_ENTER>(c, a, rows, batch, st))) {
     return rc;
+  }
+  if (skip_b_f64 && nf > 0) {
+    *skip_b_f64 = nf;
+    if (nf < rows)
+      return launch_fast_B_rows(c, false, false, rows_from(dst, nf), rows_from(dst, nf), rows - nf, batch, prime0 + nf, st_int);
+    return 0;
   }
   if (st_int != st && nf > 0) {  // pass B split by hand: FP64 rows on st, the rest on st_int
     if ((rc = launch_fast_B_rows(c, false, true, dst, dst, nf, batch, prime0, st))) return rc;
@@ -1959,10 +1976,14 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
     if (rc) return rc;
     sst = (tb200_stream)c->side;
   }
+  // the last operand's pass B runs fused with the tensor product on the FP64 rows (k_fast_fwd_B_tensor)
+  const bool fuse = fast && !square && c->fused_tensor && c->LB == 8;
+  int nfused = 0;
   for (int i = 0; i < (square ? 2 : 4); ++i) {
     TbView xi = dense(x + i * pe, L, N);
     if (fast) {
-      int rc = fast_forward_enter(c, in[i], xi, L, nb, lvl, pre_rescale ? level : -1, st, sst);
+      int rc = fast_forward_enter(c, in[i], xi, L, nb, lvl, pre_rescale ? level : -1, st, sst,
+                                  (fuse && i == 3) ? &nfused : nullptr);
       if (rc) return rc;
     } else if (pre_rescale) {
       rescale_impl(c, level, nb, in[i], xi, 1, st);
@@ -1977,9 +1998,18 @@ static int mult_front(tb200_ctx* c, int level, int nb, TbView a0, TbView a1, TbV
     int rc = side_stream_join(c, st);
     if (rc) return rc;
   }
-  LAUNCH(k_tensor, grid_pw(c, L, nb, 2), dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(), dense(x, L, N),
-         dense(x + pe, L, N), dense(x + (square ? 0 : 2) * pe, L, N), dense(x + (square ? 1 : 3) * pe, L, N), d0, d1,
-         d2, lvl, N);
+  if (nfused > 0) {
+    const int te = N < TB_TILE ? N : TB_TILE;
+    auto kfn = k_fast_fwd_B_tensor<8>;
+    LAUNCHN("k_fast_fwd_B_tensor", kfn, dim3((unsigned)(N / te), (unsigned)nfused, (unsigned)nb), dim3((unsigned)(te / 16)), st,
+            c->devf(), dense(x + 3 * pe, L, N), dense(x, L, N), dense(x + pe, L, N), dense(x + 2 * pe, L, N), d0, d1, d2, lvl);
+    if (nfused == L) return 0;
+  }
+  const int r0 = nfused;  // rows left to the stand-alone tensor product (60-bit limbs; every row without the fusion)
+  LAUNCH(k_tensor, grid_pw(c, L - r0, nb, 2), dim3(N / 2 < 256 ? N / 2 : 256), st, c->dev(),
+         rows_from(dense(x, L, N), r0), rows_from(dense(x + pe, L, N), r0),
+         rows_from(dense(x + (square ? 0 : 2) * pe, L, N), r0), rows_from(dense(x + (square ? 1 : 3) * pe, L, N), r0),
+         rows_from(d0, r0), rows_from(d1, r0), rows_from(d2, r0), lvl + r0, N);
   return 0;
 }
 

@@ -86,6 +86,7 @@ struct tb200_ctx {
   int fast = 1;
   int fused_core = 1;        // FP64 limbs: pass B + key inner product + inverse pass B' in one kernel
   int fused_moddown = 0;     // ModDown + tail inside the exit of inverse pass A' of the ordinary limbs (measured slower)
+  int fused_tensor = 1;      // cc_mult: pass B of the last operand + tensor product in one kernel on the FP64 limbs
   int sum_ntt = 1;           // exposed forward NTT: deferred-reduction kernels for lazy inputs on the FP64 limbs
   int stream_ws = 1;         // engine-call scratch leased from the stream-ordered pool on the caller's stream
   int side_rows = 0;         // the 60-bit limb rows of a key switch run on a forked stream beside the FP64 rows

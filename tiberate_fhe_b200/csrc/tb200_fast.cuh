@@ -34,6 +34,7 @@ struct __align__(16) TbFastPrime {
   double exd, nid;   // ex and N^-1 mod q, centred into (-q/2, q/2]
   double Rcd, cPd;   // R mod q and P mod q (P = product of the special primes) centred
   u64 c96;           // 2^96 mod q (tb_montred_wide)
+  double Rid;        // R^-1 mod q centred (k_fast_fwd_B_tensor: Montgomery products on the FP64 pipe)
 };
 
 namespace tb {

@@ -325,6 +325,67 @@ __global__ void __launch_bounds__(256, F64ONLY ? TB_F64_MINB : 3) k_fast_fwd_B(T
   }
 }
 
+// Forward pass B of the LAST operand of a ciphertext product fused with the tensor product (ckks_engine.py:1669-1675),
+// FP64 limbs only: the transformed y1 tile never goes to HBM -- it meets the three operands transformed before it
+// (x0, x1, y0: canonical Montgomery-form integers) in the coalesced layout and the thread writes d0 = x0 y0,
+// d1 = x0 y1 + x1 y0, d2 = x1 y1 (Montgomery products a b R^-1 as two error-free FP64 products; canonical integers,
+// which the consumers -- key inner product, own-limb reads, inverse pass B' -- take like the lazy values of k_tensor).
+// The tensor product alone is HBM-bound (7 limb passes); fused, the transform's FP64 work runs under that traffic and
+// one write + one read of y1 disappear.
+template <int LB>
+__global__ void __launch_bounds__(256, 3) k_fast_fwd_B_tensor(TbDevFast c, TbView src, TbView x0, TbView x1, TbView y0,
+                                                              TbView d0, TbView d1, TbView d2, int prime0) {
+  TB_KERNEL_SHARED i64 sm[TB_SMEM_SLOTS];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int limb = blockIdx.y, g = prime0 + limb, z = blockIdx.z;
+  const TbFastPrime P = c.fp[g];
+  const long e0 = (long)blockIdx.x * nt * 16;
+  const int blk = tid >> (LB - 4), lt = tid & ((1 << (LB - 4)) - 1);
+  const int tile = (int)(e0 >> LB) + blk;
+  auto slot = [&](int lx) { return tb::pad16((blk << LB) | lx); };
+  constexpr int f0 = tb::fwd_field<LB>(0);
+  const tb::FastF64Pol pol{P.qd, P.qinv};
+  const i64* s = src.row(z, limb) + e0;
+  i64 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = s[(blk << LB) | tb::tile_x(lt, i, f0)];
+  tb::tile_fwd<LB, true>(x, sm, lt, tile, c.logN - 1, c.twd + ((long)g << c.logN), pol, slot);
+  tile_f64_reduce<false>(x, pol);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sm[slot(tb::tile_x(lt, i, 0))] = x[i];
+  __syncthreads();
+  const i64 *p0 = x0.row(z, limb) + e0, *p1 = x1.row(z, limb) + e0, *q0 = y0.row(z, limb) + e0;
+  i64 *o0 = d0.row(z, limb) + e0, *o1 = d1.row(z, limb) + e0, *o2 = d2.row(z, limb) + e0;
+  auto canon = [&](double r) {  // |r| < 1.2 q -> canonical integer
+    r = r < 0.0 ? __dadd_rn(r, pol.q) : r;
+    r = r >= pol.q ? __dadd_rn(r, -pol.q) : r;
+    return tb::FastF64Pol::to_int(r);
+  };
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = 2 * (i * nt + tid);
+    const longlong2 a0 = *reinterpret_cast<const longlong2*>(p0 + e);
+    const longlong2 a1 = *reinterpret_cast<const longlong2*>(p1 + e);
+    const longlong2 b0 = *reinterpret_cast<const longlong2*>(q0 + e);
+    const double b1x = pol.mulmod(__longlong_as_double(sm[tb::pad16(e)]), P.Rid);       // y1 R^-1
+    const double b1y = pol.mulmod(__longlong_as_double(sm[tb::pad16(e + 1)]), P.Rid);
+    const double b0x = pol.mulmod(tb::FastF64Pol::from_int(b0.x), P.Rid), b0y = pol.mulmod(tb::FastF64Pol::from_int(b0.y), P.Rid);
+    const double a0x = tb::FastF64Pol::from_int(a0.x), a0y = tb::FastF64Pol::from_int(a0.y);
+    const double a1x = tb::FastF64Pol::from_int(a1.x), a1y = tb::FastF64Pol::from_int(a1.y);
+    longlong2 o;
+    o.x = canon(pol.mulmod(a0x, b0x));
+    o.y = canon(pol.mulmod(a0y, b0y));
+    *reinterpret_cast<longlong2*>(o0 + e) = o;
+    o.x = canon(pol.reduce(__dadd_rn(pol.mulmod(a0x, b1x), pol.mulmod(a1x, b0x))));
+    o.y = canon(pol.reduce(__dadd_rn(pol.mulmod(a0y, b1y), pol.mulmod(a1y, b0y))));
+    *reinterpret_cast<longlong2*>(o1 + e) = o;
+    o.x = canon(pol.mulmod(a1x, b1x));
+    o.y = canon(pol.mulmod(a1y, b1y));
+    *reinterpret_cast<longlong2*>(o2 + e) = o;
+  }
+}
+
 // inverse pass B'.  Inputs: lazy residues in (-2q, 2q) (negatives are lifted by 2q first).
 // IN_MODE 1 (the exposed tb200_intt): FP64 limbs accept any |x| < 2^51 and are reduced first;
 // IN_MODE 2 (after k_fast_mac): FP64 limbs arrive as doubles (|x| < 16 q), reduced first.
