@@ -80,8 +80,9 @@ int tb200_ctx_set_chunk(tb200_ctx*, int chunk);
  * inner product without per-term reductions); 0: they are composed from the exact op-layer kernels with
  * the reference's own lazy Montgomery butterflies.  Outputs are bit-identical either way (every internal
  * chain ends in a canonicalising step); the switch exists for A/B tests and measurements.  The mod-q path
- * expects key-switching key residues below 2^51 in magnitude on primes below 2^42 (the reference's keys
- * are lazy Montgomery residues in (-2q, 2q)). */
+ * expects key-switching key residues below 2^51 in magnitude on primes below 2^42 and below 2^62 on larger
+ * primes (whose 128-bit key sums then hold 16 digit groups; with residues below 2^61, all 32) -- the
+ * reference's keys are lazy Montgomery residues in (-2q, 2q). */
 int tb200_ctx_set_fast(tb200_ctx*, int on);
 /* Mod-q path only: share (in eighths, 0..8; default 8 = all) of the limbs of primes below 2^42 whose
  * arithmetic runs on the FP64 pipe (exact-integer doubles, 6 DFMA-class instructions per modular product)
